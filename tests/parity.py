@@ -1,0 +1,68 @@
+"""Shared parity helpers (test infrastructure).
+
+The parity bar (BASELINE.json north_star): trajectories within 1e-6 degrees and identical
+accepted-step counts for NON-GRAZING rays; identical NaN (termination) patterns.  The non-grazing
+mask comes with each golden fixture (made by oracle/make_golden.py from two runs of the unmodified
+reference) or, for cases without a fixture, from two runs of the oracle (`oracle_nongrazing`).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = ("rlon", "rlat", "rzwn", "rmwn", "ramp", "rug", "rvg")
+TOL_DEG = 1e-6          # the tolerance north_star states for floating point
+REL_TOL_STATE = 1e-7    # k, l, A, ug, vg relative tolerance on the non-grazing set
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+
+
+def background(g):
+    import rwrt_b200  # noqa: F401
+    from rwrt_b200 import synthetic
+    import ast
+    import hashlib
+    kw = ast.literal_eval(str(g["bg_kwargs"]))
+    u, v = getattr(synthetic, str(g["background"]))(**kw)
+    assert hashlib.sha256(u.tobytes()).hexdigest() == str(g["u_sha"]), "synthetic background drifted"
+    assert hashlib.sha256(v.tobytes()).hexdigest() == str(g["v_sha"]), "synthetic background drifted"
+    return u, v
+
+
+def compare(got, got_accepted, ref, ref_accepted, nongrazing, label=""):
+    """got/ref: dict name -> (nt, 3, ns, nz).  Returns a stats dict; raises AssertionError on failure."""
+    live = ~np.isnan(ref["rmwn"][0])
+    sel = nongrazing & live
+    # 1. termination / NaN patterns: identical on the non-grazing set (and for dead slots everywhere)
+    for n in NAMES:
+        a, b = np.isnan(got[n]), np.isnan(ref[n])
+        bad = (a != b).any(axis=0)
+        assert not (bad & (sel | ~live)).any(), f"{label}: NaN pattern of {n} differs on {int((bad & (sel | ~live)).sum())} non-grazing slots"
+    # 2. NaN-root slots keep the reference's constant pattern bit for bit
+    for n in ("rlon", "rlat", "rzwn"):
+        assert np.array_equal(got[n][:, ~live], ref[n][:, ~live], equal_nan=True), f"{label}: {n} on NaN-root slots"
+    # 3. positions within 1e-6 degrees at every output time
+    with np.errstate(invalid="ignore"):
+        dpos = np.maximum(np.abs(got["rlon"] - ref["rlon"]), np.abs(got["rlat"] - ref["rlat"]))
+    dpos = np.degrees(np.where(np.isnan(dpos), 0.0, dpos)).max(axis=0)
+    assert (dpos[sel] < TOL_DEG).all(), f"{label}: {int((dpos[sel] >= TOL_DEG).sum())} non-grazing rays deviate > 1e-6 deg (max {dpos[sel].max():.3g})"
+    # 4. the other state components and the group velocity, relative
+    worst_rel = 0.0
+    for n in ("rzwn", "rmwn", "ramp", "rug", "rvg"):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            rel = np.abs(got[n] - ref[n]) / np.maximum(np.abs(ref[n]), 1e-3)
+        rel = np.where(np.isnan(rel), 0.0, rel).max(axis=0)
+        worst_rel = max(worst_rel, float(rel[sel].max()) if sel.any() else 0.0)
+        assert (rel[sel] < REL_TOL_STATE * 1e2).all(), f"{label}: {n} relative deviation {rel[sel].max():.3g} on the non-grazing set"
+    # 5. accepted-step counts identical
+    assert np.array_equal(got_accepted[sel], ref_accepted[sel]), f"{label}: accepted-step counts differ on {int((got_accepted[sel] != ref_accepted[sel]).sum())} non-grazing rays"
+    assert (got_accepted[~live] == 0).all(), f"{label}: NaN-root slots must count zero steps"
+    return dict(slots=int(live.size), live=int(live.sum()), nongrazing=int(sel.sum()),
+                max_dev_deg_nongrazing=float(dpos[sel].max()) if sel.any() else 0.0,
+                worst_rel_state=worst_rel,
+                grazing_within_tol=int(((dpos < TOL_DEG) & live & ~nongrazing).sum()),
+                steps_total=int(got_accepted.sum()), steps_total_ref=int(ref_accepted.sum()))
