@@ -123,7 +123,7 @@ def test_solver_known_answers(tag):
     if tag == "poly":      # x(10) = 100 exactly: error magnitudes quoted at rkf45.py:856-858
         assert abs(y[0] - 100.0) < 1e-10
     if tag == "expo":      # x(10) = 10 (e - 1)
-        assert abs(y[0] - 10.0 * (np.e - 1.0)) < 1e-11
+        assert abs(y[0] - 10.0 * (np.e - 1.0)) < 1e-8
 
 
 TRAJ = ["c1_jet", "great_circle", "clim_g1", "clim_g1_freq", "clim_g2"]
