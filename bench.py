@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- accepted RK45 ray-steps per second (fp64) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA engine behind the C ABI)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the reference algorithm on host cores
+
+One "step" = one pass of the ray path (WR.ray_run: t=0 state + RK45 integration of every ray) over
+one batch of synthetic sources.  Workload = BASELINE.json configs[1]: global 1-degree synthetic
+climatological background ("Clim", seed 20250327), sources at every grid point with |lat| <= 88 deg
+(63 720 sources), k = 1..6, stationary, 30 days, tstep 2 h  ->  1 146 960 ray slots, nt = 361,
+7 x 361 x 1 146 960 x 8 B = 23.2 GB of trajectories per step.
+
+JSON keys: see the contract in the task statement; `roofline.bound` is "fp64" because the hot kernel
+is bound by the FP64 (DFMA) pipe, not by HBM or the tensor cores; an `hbm` view of
+the same kernel is given in `roofline.hbm` for completeness.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_STEP = 1342.0          # 6 RHS x 167 + 340 step algebra (algorithmic fp64 flop)
+BYTES_PER_OUTPUT = 56.0         # 7 doubles written per (ray, output time)
+NOMINAL_FP64_TFLOPS = 37.2      # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+
+
+def workload(name, rank=0):
+    """Returns dict(u, v, lon, lat, src_lon_deg, src_lat_deg, zwn, days)."""
+    import rwrt_b200  # noqa: F401
+    from rwrt_b200 import synthetic
+    if name == "c2":
+        nlon, nlat = 360, 181
+        u, v = synthetic.clim(nlon, nlat)
+        slon, slat = synthetic.all_gridpoint_sources(nlon, nlat, 88.0)
+        # weak scaling: every rank integrates a full C2-sized source set, shifted by a fraction of a cell
+        slon = (slon + 0.37 * rank / 8.0) % 360.0
+        zwn, days = np.arange(1.0, 7.0), 30.0
+    elif name == "c2-small":      # same physics, 1/16 of the sources: quick checks
+        nlon, nlat = 360, 181
+        u, v = synthetic.clim(nlon, nlat)
+        slon, slat = synthetic.all_gridpoint_sources(nlon, nlat, 88.0)
+        slon, slat = slon[rank % 16::16], slat[rank % 16::16]
+        zwn, days = np.arange(1.0, 7.0), 30.0
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    lon, lat = synthetic.grid_coords(nlon, nlat)
+    return dict(u=u, v=v, lon=lon, lat=lat, src_lon_deg=slon, src_lat_deg=slat, zwn=zwn, days=days,
+                nlon=nlon, nlat=nlat)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on the host cores (oracle C restatement)
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    wl_name, idx, days = args
+    from oracle import oracle
+    wl = workload(wl_name)
+    F = oracle.bs_ready(wl["u"], wl["v"], wl["lat"], True)
+    slon, slat = np.radians(wl["src_lon_deg"][idx]), np.radians(wl["src_lat_deg"][idx])
+    nt = int(days * 86400.0 / 7200.0) + 1
+    t0 = time.perf_counter()
+    out = oracle.ray_init(F, wl["lon"], wl["lat"], slon, slat, wl["zwn"], 0.0, nt)
+    acc, _ = oracle.ray_run_rk45(F, wl["lon"], wl["lat"], out, 7200.0, days * 86400.0)
+    return int(acc.sum()), time.perf_counter() - t0
+
+
+def cpu_sample(wl_name, nsrc, cores, seed=0):
+    """Time the oracle on a seeded random sample of `nsrc` sources of the workload, on `cores` processes."""
+    import multiprocessing as mp
+    wl = workload(wl_name)
+    rng = np.random.default_rng(seed)
+    idx = np.sort(rng.choice(len(wl["src_lon_deg"]), size=min(nsrc, len(wl["src_lon_deg"])), replace=False))
+    parts = [p for p in np.array_split(idx, cores) if len(p)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker((wl_name, parts[0], wl["days"]))]
+    else:
+        with mp.get_context("fork").Pool(len(parts)) as pool:
+            res = pool.map(_cpu_worker, [(wl_name, p, wl["days"]) for p in parts])
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return steps, slowest, wall, len(idx)
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import build_oracle
+    build_oracle.build()
+    cores = os.cpu_count() or 1
+    cores = min(cores, 64)
+    nsrc = a.ref_sources or max(240, 120 * cores)
+    vals = []
+    for i in range(a.warmup + a.steps):
+        steps, slowest, wall, n = cpu_sample(a.workload, nsrc, cores, seed=i)
+        if i >= a.warmup:
+            vals.append((steps, slowest))
+    steps = sum(v[0] for v in vals)
+    secs = sum(v[1] for v in vals)
+    value = steps / secs
+    sample = (f"seeded random sample of {n} of the {a.workload} sources per step, split over {cores} processes "
+              f"(oracle C restatement of the reference algorithm, gcc -O2 -ffp-contract=off; the Python reference "
+              f"itself cannot travel to this box: see DESIGN.md)")
+    line = {"impl": "reference", "metric": "accepted RK45 ray-steps/s (fp64)", "value": value, "unit": "steps/s",
+            "n_gpus": 0, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": a.workload, "sample_sources_per_step": n},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import rwrt_b200  # noqa: F401
+    from rwrt_b200 import build as rbuild
+    from rwrt_b200 import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        rbuild.build()
+    if world > 1:
+        dist.barrier()
+    lib.require_gpu()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = lib.load()
+    wl = workload(a.workload, rank)
+    nlon, nlat = wl["nlon"], wl["nlat"]
+    nsource, nzwn = len(wl["src_lon_deg"]), len(wl["zwn"])
+    tstep, ttotal = 7200.0, wl["days"] * 86400.0
+    nt = int(ttotal / tstep) + 1
+    N = 3 * nsource * nzwn
+    slon = np.radians(wl["src_lon_deg"]); slat = np.radians(wl["src_lat_deg"])
+    flags = lib.MODE_STRICT if a.strict else lib.MODE_FAST
+
+    h = lib.vp()
+    lib.check(L.rwrt_create(local, nlon, nlat, 1, 1, C.byref(h)), "rwrt_create")
+    stream = torch.cuda.current_stream()
+    sp = lib.vp(stream.cuda_stream)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
+         dict(u=wl["u"], v=wl["v"], lon=wl["lon"], lat=wl["lat"], cl=np.cos(wl["lat"]), sl=np.sin(wl["lat"]),
+              slon=slon, slat=slat, zwn=wl["zwn"]).items()}
+    lib.check(L.rwrt_bs_ready(h, lib.ptr(d["u"]), lib.ptr(d["v"]), lib.ptr(d["lon"]), lib.ptr(d["lat"]),
+                              lib.ptr(d["cl"]), lib.ptr(d["sl"]), None, None, sp), "rwrt_bs_ready")
+    out = torch.empty((7, nt, N), dtype=torch.float64, device=dev)
+    acc = torch.zeros(N, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def one_step():
+        lib.check(L.rwrt_ray_init(h, nsource, lib.ptr(d["slon"]), lib.ptr(d["slat"]), None, nzwn, lib.ptr(d["zwn"]),
+                                  0.0, nt, lib.ptr(out), sp), "rwrt_ray_init")
+        lib.check(L.rwrt_ray_run_rk45(h, nsource, None, nzwn, nt, tstep, ttotal, 1e-6, 1e-6, 1e-3, 0.1, flags,
+                                      lib.ptr(out), lib.ptr(acc), None, None, lib.ptr(total), sp), "rwrt_ray_run_rk45")
+
+    stats = (C.c_double * 3)()
+    for _ in range(a.warmup):
+        one_step()
+        flush.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kern_ms, steps_done, launches = [], 0, 0
+    torch.cuda.synchronize()
+    for i in range(a.steps):
+        ev[i][0].record(stream)
+        one_step()
+        ev[i][1].record(stream)
+        flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
+        L.rwrt_last_run_stats(h, stats)     # syncs on the integrate kernels' end event
+        launches += int(stats[0]) + 1       # + ray_init
+        kern_ms.append(stats[2])
+        steps_done += int(total.item())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    s = torch.tensor([float(steps_done)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    ms_max, steps_all = float(t.item()), float(s.item())
+    value = steps_all / (ms_max * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI call (H2D of inputs, D2H of the 7 result arrays) ----
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags, world, dev)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (rk45_integrate; prepare + fill are inside the same event pair) ----
+    peak_tf = C.c_double(0)
+    L.rwrt_measure_fp64_peak(h, C.byref(peak_tf))
+    kms = float(np.mean(kern_ms))
+    steps_per_launch = steps_done / a.steps
+    achieved_tf = steps_per_launch * FLOP_PER_STEP / (kms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    live_outputs = None
+    hbm_alg = steps_per_launch / 1.07 * BYTES_PER_OUTPUT   # ~1.07 accepted steps per (ray, output time)
+    roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf.value or NOMINAL_FP64_TFLOPS,
+            "unit": "TFLOP/s", "frac": achieved_tf / (peak_tf.value or NOMINAL_FP64_TFLOPS),
+            "peak_source": "measured DFMA-chain microbenchmark in this run (rwrt_measure_fp64_peak); nominal 37.2",
+            "flop_per_step": FLOP_PER_STEP, "kernel_ms": kms, "traffic": None,
+            "hbm": {"achieved": hbm_alg / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_alg / (kms * 1e-3) / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    # ---- CPU baseline: the oracle port on one core, bounded sample ----
+    cpu = None
+    if not a.no_cpu:
+        from oracle import build_oracle
+        build_oracle.build()
+        st, slowest, wall, n = cpu_sample(a.workload, a.cpu_sources, 1, seed=0)
+        cpu = {"value": st / slowest, "unit": "steps/s", "cores": 1, "kind": "port",
+               "sample": f"seeded random sample of {n} sources of the workload ({st} accepted steps, {slowest:.1f} s), "
+                         "oracle C restatement, single thread"}
+    line = {"metric": "accepted RK45 ray-steps/s (fp64)", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{a.workload}: Clim 1deg background, {nsource} sources x k=1..{nzwn} x 3 roots = {N} "
+                                   f"ray slots per GPU, {wl['days']:.0f} d, tstep 2 h, nt={nt}, rtol=atol=1e-6",
+                       "mode": "strict" if a.strict else "fast", "accepted_steps_per_step_per_gpu": steps_per_launch,
+                       "l2": "flushed between timed iterations (256 MB write); outputs (23 GB) exceed L2 anyway",
+                       "timed_region": "rwrt_ray_init + rwrt_ray_run_rk45 (fields resident in HBM)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    L.rwrt_destroy(h)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags, world, dev):
+    """Same metric through rwrt_real2d_host: host inputs, pinned host outputs, copies inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    from rwrt_b200 import lib
+    nbytes = 7 * nt * N * 8
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    if avail and avail < 2.5 * nbytes * max(1, world):
+        return {"value": None, "unit": "steps/s", "note": f"skipped: {avail/1e9:.0f} GB host RAM available, "
+                f"{nbytes/1e9:.1f} GB pinned result arrays needed per GPU"}
+    host = torch.empty(7 * nt * N, dtype=torch.float64, pin_memory=True)
+    acc_h = torch.empty(N, dtype=torch.int64, pin_memory=True)
+    tot_h = torch.zeros(1, dtype=torch.int64, pin_memory=True)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
+           dict(u=wl["u"], v=wl["v"], lon=wl["lon"], lat=wl["lat"], cl=np.cos(wl["lat"]), sl=np.sin(wl["lat"]),
+                slon=slon, slat=slat, zwn=wl["zwn"]).items()}
+    h2d = sum(t.numel() * t.element_size() for t in pin.values())
+    d2h = nbytes + N * 8 + 8
+
+    def call():
+        lib.check(L.rwrt_real2d_host(h, lib.ptr(pin["u"]), lib.ptr(pin["v"]), lib.ptr(pin["lon"]), lib.ptr(pin["lat"]),
+                                     lib.ptr(pin["cl"]), lib.ptr(pin["sl"]), nsource, lib.ptr(pin["slon"]),
+                                     lib.ptr(pin["slat"]), None, nzwn, lib.ptr(pin["zwn"]), 0.0, nt, tstep, ttotal,
+                                     1e-6, 1e-6, 1e-3, 0.1, flags, lib.ptr(host), lib.ptr(acc_h), None,
+                                     lib.ptr(tot_h), None), "rwrt_real2d_host")
+
+    call()                                   # warm-up (first touch of the pinned pages)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = max(1, min(a.steps, 3))
+    t0 = time.perf_counter()
+    steps = 0
+    for _ in range(reps):
+        call()                               # synchronises before returning
+        steps += int(tot_h.item())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    s = torch.tensor([float(steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return {"value": float(s.item()) / float(t.item()), "unit": "steps/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(t.item()) / reps,
+            "api": "rwrt_real2d_host (C ABI, host pointers; pinned result arrays)"}
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="c2")
+    p.add_argument("--strict", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--cpu-sources", type=int, default=2000)
+    p.add_argument("--ref-sources", type=int, default=0)
+    a = p.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

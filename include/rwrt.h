@@ -1,0 +1,158 @@
+/*
+ * rwrt.h -- C ABI of librwrt.so, the B200 (sm_100a) ray-integration engine.
+ *
+ * Drop-in boundary for the RK45 ray path of yinan-codes/Rossby-wave-ray-tracing.  The reference
+ * is pure Python; its "FFI" for this path is the set of Python calls listed beside each entry
+ * point (file:line into the reference).  A maintainer binds these symbols with ctypes
+ * (INTEGRATION.md shows the stub); `rossby-wave-ray-tracing_b200/lib.py` is that binding.
+ *
+ * Conventions
+ *   - plain C types only; every array argument is a DEVICE pointer unless the function name ends
+ *     in `_host` (those take host pointers and do their own H2D / D2H on the given stream);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     stream-ordered and return without synchronising unless documented otherwise;
+ *   - return value: 0 = ok, negative = error (rwrt_status); rwrt_last_error() gives a
+ *     thread-local message.  No C++ exception crosses the boundary;
+ *   - the caller owns every buffer it passes in; the handle owns only its private field copies
+ *     and work lists, released by rwrt_destroy;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     RWRT_ERR_CUDA.
+ *
+ * Array layouts are the reference's own: grids are [i_lon][j_lat] (bs.py:245-247); the seven ray
+ * result arrays are (nt, 3, nsource, nzwn) C-order, zwn fastest (wr.py:160-167); a "slot" is the
+ * flattened (root, source, zwn) index.
+ */
+#ifndef RWRT_H
+#define RWRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RWRT_ABI_VERSION 1
+
+typedef struct rwrt_ctx *rwrt_handle;
+
+typedef enum {
+    RWRT_OK = 0,
+    RWRT_ERR_ARG = -1,   /* bad argument (the facade raises the reference's ValueError)      */
+    RWRT_ERR_CUDA = -2,  /* CUDA runtime error / no device                                    */
+    RWRT_ERR_STATE = -3, /* call order: e.g. ray_init before bs_ready                         */
+    RWRT_ERR_NOMEM = -4
+} rwrt_status;
+
+/* flags for rwrt_ray_run_rk45 */
+#define RWRT_MODE_FAST 0u   /* FMA contraction allowed (default)                              */
+#define RWRT_MODE_STRICT 1u /* every operation a separate IEEE double op, reference order    */
+#define RWRT_RECORD_LAYOUT 2u /* internal: keep trajectories as per-ray records (no transpose) */
+
+/* per-slot status codes written by rwrt_ray_run_rk45 (new, additive: the reference only has NaN) */
+#define RWRT_RAY_NO_ROOT 0   /* NaN root at t = 0: never propagates   */
+#define RWRT_RAY_ALIVE 1     /* reached ttotal                                                 */
+#define RWRT_RAY_POLE 2      /* |lat| >= pi/2 at an output time           (wr.py:838-843)      */
+#define RWRT_RAY_SPEED 3     /* moved >= cut_off between two outputs      (wr.py:844-850)      */
+#define RWRT_RAY_NAN 4       /* state became NaN while stepping: |l| >= 100 critical line or
+                                pole inside a step (wr.py:508-514, rkf45.py:400-403, 446)     */
+
+int rwrt_abi_version(void);
+const char *rwrt_last_error(void);
+int rwrt_device_count(int *count);
+
+/* Library-owned pinned host memory (for result arrays that are copied back asynchronously). */
+int rwrt_host_alloc(void **ptr, size_t bytes);
+int rwrt_host_free(void *ptr);
+
+/*
+ * One handle per (device, background grid).  Replaces WR.__init__ -> BS.__init__ (wr.py:133-171,
+ * bs.py:70-112).  nmember > 1 batches an ensemble of background states on the same grid.
+ */
+int rwrt_create(int device, int nlon, int nlat, int xcyclic, int nmember, rwrt_handle *out);
+int rwrt_destroy(rwrt_handle h);
+
+/*
+ * BS.ready(xcyclic) (bs.py:318-407): finite-difference derivative fields, 9-point smoothing,
+ * stacking.  u, v: (nmember, nlon, nlat) float32.  lon (nlon), lat (nlat) float64 radians: the
+ * coordinate arrays the sampler indexes with (interpolation.py:78-82).  coslat/sinlat (nlat):
+ * optional tables (NULL = computed on the device); the facade passes NumPy's values so that the
+ * fields are bit-identical to the reference's.
+ * Outputs (either may be NULL): fields18 (nmember, nlon + xcyclic, nlat, 18) in the reference's
+ * order (bs.py:349-372); diag9 (nmember, 9, nlon, nlat): q, uxx, uyy, vxx, vyy, uxy, vxy, betam, KS.
+ * The handle keeps its own packed copy of the 11 fields the ray equations consume.
+ */
+int rwrt_bs_ready(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
+                  const double *coslat, const double *sinlat, double *fields18, double *diag9, void *stream);
+
+/* BS.read_from_precaled_nc analogue (bs.py:409-454): adopt externally computed fields18. */
+int rwrt_bs_set_fields(rwrt_handle h, const double *fields18, const double *lon, const double *lat, void *stream);
+
+/*
+ * BS.cal_bs_mercator_point(lon, lat, mode='numpy') (bs.py:781-887): bilinear sample of the fields
+ * at n points + Mercator transform.  out: (12, n) = fmu, fmv, fmux, fmuy, fmvx, fmvy, fmqx, fmqy,
+ * fmqxx, fmqxy, fmqyx, fmqyy (the rows the ray path uses).  member: NULL or (n) int32.
+ */
+int rwrt_sample_mercator(rwrt_handle h, int64_t n, const double *lon, const double *lat, const int32_t *member,
+                         double *out, void *stream);
+
+/* One right-hand side per point: WR.diffun_numpy (wr.py:492-556).  y, dy: (5, n). */
+int rwrt_rhs(rwrt_handle h, int64_t n, const double *y, const int32_t *member, double *dy, uint32_t flags,
+             void *stream);
+
+/*
+ * WR.ray_initial_numpy (wr.py:344-395) + cal_ky_numpy / change_roots_order (bs.py:942-1040):
+ * writes row 0 of the seven planes of out7 = (7, nt, 3, nsource, nzwn).  src_lon/src_lat radians.
+ * src_member: NULL or (nsource) int32 ensemble member of each source.
+ */
+int rwrt_ray_init(rwrt_handle h, int nsource, const double *src_lon, const double *src_lat,
+                  const int32_t *src_member, int nzwn, const double *zwn, double freq, int nt, double *out7,
+                  void *stream);
+
+/*
+ * WR.core_ray_run_rk45 (wr.py:767-887) driving RK45 (rkf45.py:222-514): integrates every slot from
+ * row 0 of out7 to ttotal, writing rows 1..nt-1.  tstep/ttotal in seconds; cut_off as in
+ * WR.__init__ (0.1).  accepted / attempts: (3*nsource*nzwn) int64, status: int8 -- all optional.
+ * total_accepted (optional, device int64[1]) receives the sum of accepted steps (the metric).
+ */
+int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
+                      double ttotal, double rtol, double atol, double min_step_factor, double cut_off,
+                      uint32_t flags, double *out7, int64_t *accepted, int64_t *attempts, int8_t *status,
+                      int64_t *total_accepted, void *stream);
+
+/*
+ * Ray-density / wave-ray-flux gridding of trajectories (manual section 4; no reference code --
+ * parity unpinned, defined by oracle/gridding.py).  The domain is three longitude circles
+ * [-360, 720) deg x [-90, 90] deg with cells of (dlon_deg, dlat_deg).  For every output time it >= 1
+ * and every live sample: count[cell] += 1 (int64), flux_x/flux_y[cell] += round(ug|vg * 2^20) (int64
+ * fixed point, so that the sums are order independent and bit exact across GPUs).
+ * count, fx, fy: (ncx, ncy) int64 with ncx = ceil(1080/dlon_deg), ncy = ceil(180/dlat_deg).
+ */
+int rwrt_grid_accumulate(rwrt_handle h, int64_t nslot, int nt, const double *out7, double dlon_deg, double dlat_deg,
+                         int ncx, int ncy, int64_t *count, int64_t *fx, int64_t *fy, void *stream);
+
+/*
+ * Whole ray path with HOST buffers (the call main_wr.real2d_hnf makes, main_wr.py:66-89, minus
+ * NetCDF): H2D of u, v, coordinates, sources; BS.ready; ray_initial; RK45; D2H of the seven
+ * result arrays (pinned memory from rwrt_host_alloc makes the copy-back asynchronous and
+ * chunk-overlapped with the integration).  Synchronises before returning.
+ */
+int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
+                     const double *coslat, const double *sinlat, int nsource, const double *src_lon,
+                     const double *src_lat, const int32_t *src_member, int nzwn, const double *zwn, double freq,
+                     int nt, double tstep, double ttotal, double rtol, double atol, double min_step_factor,
+                     double cut_off, uint32_t flags, double *out7_host, int64_t *accepted_host,
+                     int8_t *status_host, int64_t *total_accepted_host, void *stream);
+
+/* counters of the last rwrt_ray_run_rk45 on this handle (host side, after a sync):
+ * [0] kernels launched, [1] live rays, [2] ms of the integrate kernel(s) by CUDA events */
+int rwrt_last_run_stats(rwrt_handle h, double *stats3);
+
+/* Roofline denominator: measured FP64 FMA throughput of the device (TFLOP/s, register-resident DFMA
+ * chains).  Diagnostic only; used by bench.py next to MEASURED_PEAKS.json, which has no FP64 figure. */
+int rwrt_measure_fp64_peak(rwrt_handle h, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RWRT_H */

@@ -480,11 +480,8 @@ static int64_t advance_to(rhs_fn fn, const void *ctx, rk_state *s, double t_boun
         int rejected = 0;
         double t_new, h;
         for (;;) {
-            if (isnan(h_abs)) { /* rkf45.py:423-425 would abort the whole batch; per-ray: park */
-                s->t = t_bound;
-                for (int c = 0; c < n; ++c) s->y[c] = NAN;
-                return acc;
-            }
+            /* a NaN step (rkf45.py:423-425 aborts only when EVERY pending ray has one) flows through:
+             * t_new = NaN, the stages are NaN, the error norm is NaN -> 0 -> accepted (rkf45.py:446) */
             t_new = s->t + h_abs;                             /* rkf45.py:426-435 */
             if (t_new - t_bound > 0) t_new = t_bound;
             h = t_new - s->t;
@@ -529,7 +526,7 @@ static int64_t advance_to(rhs_fn fn, const void *ctx, rk_state *s, double t_boun
             h_abs *= factor;
             rejected = 1;
         }
-        s->t = t_new;
+        s->t = isnan(t_new) ? t_bound : t_new;                /* rkf45.py:503 */
         s->h_abs = h_abs;
         for (int c = 0; c < n; ++c) s->y[c] = yn[c];
         ++acc;

@@ -1,0 +1,549 @@
+// rwrt_api.cu -- the C ABI of librwrt.so (include/rwrt.h): handle, buffers, launch sequencing.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/rwrt.h"
+#include "rwrt_internal.h"
+#include "rwrt_rk45_params.h"
+
+using namespace rwrt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(RWRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        cap = bytes;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct rwrt_ctx {
+    int device = 0, nlon = 0, nlat = 0, xcyclic = 1, nmember = 1, nlon_f = 0;
+    int sm_count = 0;
+    bool ready = false;
+    double lon0 = 0, dlon = 0, lat0 = 0, dlat = 0;
+    DevBuf fpk, scratch, trig, live, state, counters, blockcnt;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    double last_launches = 0, last_nlive = 0;
+
+    Grid grid() const
+    {
+        Grid g;
+        g.fpk = (const double *)fpk.p;
+        g.member_stride = (size_t)nlon_f * nlat * NPK;
+        g.nlon_f = nlon_f;
+        g.nlat = nlat;
+        g.lon0 = lon0;
+        g.dlon = dlon;
+        g.lat0 = lat0;
+        g.dlat = dlat;
+        return g;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// live-slot compaction (deterministic: live[] is in ascending slot order)
+// ---------------------------------------------------------------------------------------------
+namespace rwrt {
+namespace {
+
+__device__ __forceinline__ bool slot_is_live(const double *out, size_t pl, long long slot)
+{
+    // a slot is integrated iff its t=0 state has no NaN: np.mean(y) is not NaN (rkf45.py:400-402)
+    double s = out[slot] + out[pl + slot] + out[2 * pl + slot] + out[3 * pl + slot] + out[4 * pl + slot];
+    return s == s;
+}
+
+__global__ void __launch_bounds__(256) count_live_kernel(long long N, size_t pl, const double *out, int *block_counts)
+{
+    long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
+    bool live = slot < N && slot_is_live(out, pl, slot);
+    int c = __syncthreads_count(live);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(int nblocks, int *block_counts, unsigned long long *nlive)
+{
+    // exclusive scan of block_counts in place by one block (nblocks <= a few 10^4)
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = (i < nblocks) ? block_counts[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warp_sums[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            warp_sums[threadIdx.x] = w;
+        }
+        __syncthreads();
+        int warp_off = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
+        int incl = x + warp_off;
+        int c = carry;
+        if (i < nblocks) block_counts[i] = c + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nlive = (unsigned long long)carry;
+}
+
+__global__ void __launch_bounds__(256) scatter_live_kernel(long long N, size_t pl, const double *out,
+                                                           const int *block_offsets, int32_t *live)
+{
+    __shared__ int warp_cnt[8];
+    long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
+    bool is_live = slot < N && slot_is_live(out, pl, slot);
+    unsigned m = __ballot_sync(0xffffffffu, is_live);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) warp_cnt[w] = __popc(m);
+    __syncthreads();
+    int off = block_offsets[blockIdx.x];
+    for (int k = 0; k < w; ++k) off += warp_cnt[k];
+    if (is_live) live[off + __popc(m & ((1u << l) - 1))] = (int32_t)slot;
+}
+
+}  // namespace
+
+void launch_compact_live(long long N, int nt, const double *out7, int32_t *live, unsigned long long *nlive_dev,
+                         int *block_counts, int nblocks, cudaStream_t s)
+{
+    size_t pl = (size_t)nt * N;
+    count_live_kernel<<<nblocks, 256, 0, s>>>(N, pl, out7, block_counts);
+    scan_blocks_kernel<<<1, 1024, 0, s>>>(nblocks, block_counts, nlive_dev);
+    scatter_live_kernel<<<nblocks, 256, 0, s>>>(N, pl, out7, block_counts, live);
+}
+}  // namespace rwrt
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int rwrt_abi_version(void) { return RWRT_ABI_VERSION; }
+
+const char *rwrt_last_error(void) { return g_err.c_str(); }
+
+int rwrt_device_count(int *count)
+{
+    if (!count) return fail(RWRT_ERR_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(RWRT_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return RWRT_OK;
+}
+
+int rwrt_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(RWRT_ERR_ARG, "ptr is NULL");
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return RWRT_OK;
+}
+
+int rwrt_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return RWRT_OK;
+}
+
+int rwrt_create(int device, int nlon, int nlat, int xcyclic, int nmember, rwrt_handle *out)
+{
+    if (!out) return fail(RWRT_ERR_ARG, "out handle is NULL");
+    *out = nullptr;
+    if (nlon < 2 || nlat < 3 || nmember < 1) return fail(RWRT_ERR_ARG, "need nlon >= 2, nlat >= 3, nmember >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RWRT_ERR_CUDA, "no CUDA device visible: librwrt has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(RWRT_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    rwrt_ctx *h = new (std::nothrow) rwrt_ctx();
+    if (!h) return fail(RWRT_ERR_NOMEM, "host allocation failed");
+    h->device = device;
+    h->nlon = nlon;
+    h->nlat = nlat;
+    h->xcyclic = xcyclic ? 1 : 0;
+    h->nmember = nmember;
+    h->nlon_f = nlon + h->xcyclic;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    size_t npk = (size_t)nmember * h->nlon_f * nlat * NPK * sizeof(double);
+    if (h->fpk.reserve(npk) || h->trig.reserve(2 * (size_t)nlat * sizeof(double)) ||
+        h->counters.reserve(8 * sizeof(unsigned long long))) {
+        delete h;
+        return fail(RWRT_ERR_NOMEM, "device allocation of the packed fields (%zu B) failed", npk);
+    }
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    *out = h;
+    return RWRT_OK;
+}
+
+int rwrt_destroy(rwrt_handle h)
+{
+    if (!h) return RWRT_OK;
+    cudaSetDevice(h->device);
+    h->fpk.release();
+    h->scratch.release();
+    h->trig.release();
+    h->live.release();
+    h->state.release();
+    h->counters.release();
+    h->blockcnt.release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return RWRT_OK;
+}
+
+static int set_coords(rwrt_handle h, const double *lon, const double *lat, cudaStream_t s)
+{
+    // the sampler needs lon[0], lon[1]-lon[0], lat[0], lat[1]-lat[0] (interpolation.py:78-79) on the host
+    double c[4];
+    CU(cudaMemcpyAsync(c, lon, 2 * sizeof(double), cudaMemcpyDefault, s));
+    CU(cudaMemcpyAsync(c + 2, lat, 2 * sizeof(double), cudaMemcpyDefault, s));
+    CU(cudaStreamSynchronize(s));
+    h->lon0 = c[0];
+    h->dlon = c[1] - c[0];
+    h->lat0 = c[2];
+    h->dlat = c[3] - c[2];
+    return RWRT_OK;
+}
+
+int rwrt_bs_ready(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
+                  const double *coslat, const double *sinlat, double *fields18, double *diag9, void *stream)
+{
+    if (!h || !u || !v || !lon || !lat) return fail(RWRT_ERR_ARG, "rwrt_bs_ready: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->device));
+    int rc = set_coords(h, lon, lat, s);
+    if (rc) return rc;
+    size_t n = (size_t)h->nmember * h->nlon * h->nlat;
+    if (h->scratch.reserve(4 * n * sizeof(double))) return fail(RWRT_ERR_NOMEM, "scratch planes (%zu B)", 4 * n * 8);
+    double *trig = (double *)h->trig.p;
+    if (!coslat || !sinlat) {
+        launch_trig_tables(h->nlat, lat, trig, trig + h->nlat, s);
+        coslat = trig;
+        sinlat = trig + h->nlat;
+    }
+    BsArgs a;
+    a.nlon = h->nlon;
+    a.nlat = h->nlat;
+    a.nmember = h->nmember;
+    a.xcyclic = h->xcyclic;
+    a.u = u;
+    a.v = v;
+    a.coslat = coslat;
+    a.sinlat = sinlat;
+    a.q = (double *)h->scratch.p;
+    a.qxx = a.q + n;
+    a.qyy = a.q + 2 * n;
+    a.qxy = a.q + 3 * n;
+    a.fpk = (double *)h->fpk.p;
+    a.fields18 = fields18;
+    a.diag9 = diag9;
+    launch_bs_ready(a, s);
+    CU(cudaGetLastError());
+    h->ready = true;
+    return RWRT_OK;
+}
+
+int rwrt_bs_set_fields(rwrt_handle h, const double *fields18, const double *lon, const double *lat, void *stream)
+{
+    if (!h || !fields18 || !lon || !lat) return fail(RWRT_ERR_ARG, "rwrt_bs_set_fields: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->device));
+    int rc = set_coords(h, lon, lat, s);
+    if (rc) return rc;
+    launch_pack_from_fields18(h->nmember, h->nlon_f, h->nlat, fields18, (double *)h->fpk.p, s);
+    CU(cudaGetLastError());
+    h->ready = true;
+    return RWRT_OK;
+}
+
+int rwrt_sample_mercator(rwrt_handle h, int64_t n, const double *lon, const double *lat, const int32_t *member,
+                         double *out, void *stream)
+{
+    if (!h || (n > 0 && (!lon || !lat || !out))) return fail(RWRT_ERR_ARG, "rwrt_sample_mercator: NULL argument");
+    if (!h->ready) return fail(RWRT_ERR_STATE, "rwrt_sample_mercator before rwrt_bs_ready");
+    CU(cudaSetDevice(h->device));
+    launch_sample_mercator(h->grid(), n, lon, lat, member, out, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return RWRT_OK;
+}
+
+int rwrt_rhs(rwrt_handle h, int64_t n, const double *y, const int32_t *member, double *dy, uint32_t flags, void *stream)
+{
+    if (!h || (n > 0 && (!y || !dy))) return fail(RWRT_ERR_ARG, "rwrt_rhs: NULL argument");
+    if (!h->ready) return fail(RWRT_ERR_STATE, "rwrt_rhs before rwrt_bs_ready");
+    CU(cudaSetDevice(h->device));
+    if (flags & RWRT_MODE_STRICT) launch_rhs_strict(h->grid(), n, y, member, dy, (cudaStream_t)stream);
+    else launch_rhs_fast(h->grid(), n, y, member, dy, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return RWRT_OK;
+}
+
+int rwrt_ray_init(rwrt_handle h, int nsource, const double *src_lon, const double *src_lat, const int32_t *src_member,
+                  int nzwn, const double *zwn, double freq, int nt, double *out7, void *stream)
+{
+    if (!h || nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_ray_init: bad sizes");
+    if ((long long)nsource * nzwn > 0 && (!src_lon || !src_lat || !zwn || !out7))
+        return fail(RWRT_ERR_ARG, "rwrt_ray_init: NULL argument");
+    if (!h->ready) return fail(RWRT_ERR_STATE, "rwrt_ray_init before rwrt_bs_ready");
+    CU(cudaSetDevice(h->device));
+    launch_ray_init(h->grid(), nsource, src_lon, src_lat, src_member, nzwn, zwn, freq, nt, out7, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return RWRT_OK;
+}
+
+int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
+                      double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
+                      double *out7, int64_t *accepted, int64_t *attempts, int8_t *status, int64_t *total_accepted,
+                      void *stream)
+{
+    if (!h || nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45: bad sizes");
+    if (!(tstep > 0)) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45: tstep must be positive");
+    if (!h->ready) return fail(RWRT_ERR_STATE, "rwrt_ray_run_rk45 before rwrt_bs_ready");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->device));
+    long long N = 3LL * nsource * nzwn;
+    h->timed = false;
+    h->last_launches = 0;
+    h->last_nlive = 0;
+    unsigned long long *ctr = (unsigned long long *)h->counters.p;  // [0] queue, [1] total accepted, [2] nlive
+    CU(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), s));
+    if (N == 0 || nt < 2) {
+        if (total_accepted) CU(cudaMemsetAsync(total_accepted, 0, sizeof(int64_t), s));
+        return RWRT_OK;
+    }
+    if (N > 2147483647LL) return fail(RWRT_ERR_ARG, "more than 2^31-1 ray slots in one call: shard the sources");
+    if (!out7) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45: out7 is NULL");
+
+    // 1. compact the live slots
+    int nblocks = (int)((N + 255) / 256);
+    if (h->live.reserve((size_t)N * sizeof(int32_t)) || h->blockcnt.reserve((size_t)nblocks * sizeof(int)))
+        return fail(RWRT_ERR_NOMEM, "work list allocation failed");
+    launch_compact_live(N, nt, out7, (int32_t *)h->live.p, ctr + 2, (int *)h->blockcnt.p, nblocks, s);
+    unsigned long long nlive = 0;
+    CU(cudaMemcpyAsync(&nlive, ctr + 2, sizeof nlive, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));  // the one host sync of this call: grid sizes depend on nlive
+    if (nlive && h->state.reserve((size_t)nlive * 12 * sizeof(double)))
+        return fail(RWRT_ERR_NOMEM, "ray state allocation failed (%llu rays)", nlive);
+
+    // 2. parameters (rkf45.py:21-26 validate_tol; rkf45.py:362 Global_Minstep; wr.py:170 cut_off)
+    RunParams p;
+    p.g = h->grid();
+    p.src_member = src_member;
+    p.nsource = nsource;
+    p.nzwn = nzwn;
+    p.nt = nt;
+    p.N = N;
+    p.tstep = tstep;
+    p.ttotal = ttotal;
+    const double eps = 2.220446049250313e-16;
+    p.rtol = rtol < 100 * eps ? 100 * eps : rtol;
+    p.atol = atol;
+    p.gmin = fmin(min_step_factor * tstep, (tstep - 0) * 0.001);
+    p.cut = cut_off * tstep / 3600.;
+    p.out = out7;
+    p.live = (const int32_t *)h->live.p;
+    p.nlive = (long long)nlive;
+    p.state = (double *)h->state.p;
+    p.accepted = (long long *)accepted;
+    p.attempts = (long long *)attempts;
+    p.status = (signed char *)status;
+    p.queue = ctr;
+    p.total_accepted = ctr + 1;
+
+    // 3. launch: static slots, prepare, persistent integrator (one wave of resident blocks)
+    bool strict = (flags & RWRT_MODE_STRICT) != 0;
+    int per_sm = strict ? occupancy_rk45_strict() : occupancy_rk45_fast();
+    if (per_sm < 1) per_sm = 1;
+    long long want = ((long long)nlive + 127) / 128;
+    int integrate_blocks = (int)(want < (long long)per_sm * h->sm_count ? want : (long long)per_sm * h->sm_count);
+    if (integrate_blocks < 1) integrate_blocks = 1;
+    int prepare_blocks = (int)(((long long)nlive + 127) / 128);
+    int fill_blocks = (int)((N + 255) / 256);
+    CU(cudaEventRecord(h->ev0, s));
+    if (strict) launch_rk45_strict(p, prepare_blocks, fill_blocks, integrate_blocks, s);
+    else launch_rk45_fast(p, prepare_blocks, fill_blocks, integrate_blocks, s);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev1, s));
+    h->timed = true;
+    h->last_launches = 3 + (nlive ? 3 : 1);  // compaction (3) + fill + prepare + integrate
+    h->last_nlive = (double)nlive;
+    if (total_accepted)
+        CU(cudaMemcpyAsync(total_accepted, ctr + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    return RWRT_OK;
+}
+
+int rwrt_last_run_stats(rwrt_handle h, double *stats3)
+{
+    if (!h || !stats3) return fail(RWRT_ERR_ARG, "rwrt_last_run_stats: NULL argument");
+    stats3[0] = h->last_launches;
+    stats3[1] = h->last_nlive;
+    stats3[2] = 0;
+    if (h->timed) {
+        CU(cudaSetDevice(h->device));
+        CU(cudaEventSynchronize(h->ev1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        stats3[2] = ms;
+    }
+    return RWRT_OK;
+}
+
+int rwrt_measure_fp64_peak(rwrt_handle h, double *tflops)
+{
+    if (!h || !tflops) return fail(RWRT_ERR_ARG, "rwrt_measure_fp64_peak: NULL argument");
+    CU(cudaSetDevice(h->device));
+    if (measure_fp64_peak(h->sm_count, tflops, nullptr)) return fail(RWRT_ERR_CUDA, "DFMA microbenchmark failed");
+    return RWRT_OK;
+}
+
+int rwrt_grid_accumulate(rwrt_handle h, int64_t nslot, int nt, const double *out7, double dlon_deg, double dlat_deg,
+                         int ncx, int ncy, int64_t *count, int64_t *fx, int64_t *fy, void *stream)
+{
+    if (!h || !out7 || !count || !fx || !fy || nslot < 0 || nt < 1 || ncx < 1 || ncy < 1 || !(dlon_deg > 0) ||
+        !(dlat_deg > 0))
+        return fail(RWRT_ERR_ARG, "rwrt_grid_accumulate: bad argument");
+    CU(cudaSetDevice(h->device));
+    launch_grid_accumulate(nslot, nt, out7, dlon_deg, dlat_deg, ncx, ncy, (long long *)count, (long long *)fx,
+                           (long long *)fy, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return RWRT_OK;
+}
+
+int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
+                     const double *coslat, const double *sinlat, int nsource, const double *src_lon,
+                     const double *src_lat, const int32_t *src_member, int nzwn, const double *zwn, double freq, int nt,
+                     double tstep, double ttotal, double rtol, double atol, double min_step_factor, double cut_off,
+                     uint32_t flags, double *out7_host, int64_t *accepted_host, int8_t *status_host,
+                     int64_t *total_accepted_host, void *stream)
+{
+    if (!h || !u || !v || !lon || !lat || !src_lon || !src_lat || !zwn || !out7_host)
+        return fail(RWRT_ERR_ARG, "rwrt_real2d_host: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->device));
+    const size_t ng = (size_t)h->nmember * h->nlon * h->nlat;
+    const long long N = 3LL * nsource * nzwn;
+    const size_t nout = (size_t)7 * nt * N;
+    // one device arena for every input and output of the call
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    size_t o_u = carve(ng * 4), o_v = carve(ng * 4), o_lon = carve((size_t)h->nlon * 8), o_lat = carve((size_t)h->nlat * 8);
+    size_t o_cl = carve((size_t)h->nlat * 8), o_sl = carve((size_t)h->nlat * 8);
+    size_t o_slon = carve((size_t)nsource * 8), o_slat = carve((size_t)nsource * 8), o_mem = carve((size_t)nsource * 4);
+    size_t o_zwn = carve((size_t)nzwn * 8), o_acc = carve((size_t)N * 8), o_st = carve((size_t)N), o_tot = carve(8);
+    size_t o_out = carve(nout * 8);
+    char *arena = nullptr;
+    CU(cudaMalloc((void **)&arena, off));
+    int rc = RWRT_OK;
+#define CUX(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            rc = fail(RWRT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                   \
+            goto done;                                                                                  \
+        }                                                                                               \
+    } while (0)
+    CUX(cudaMemcpyAsync(arena + o_u, u, ng * 4, cudaMemcpyHostToDevice, s));
+    CUX(cudaMemcpyAsync(arena + o_v, v, ng * 4, cudaMemcpyHostToDevice, s));
+    CUX(cudaMemcpyAsync(arena + o_lon, lon, (size_t)h->nlon * 8, cudaMemcpyHostToDevice, s));
+    CUX(cudaMemcpyAsync(arena + o_lat, lat, (size_t)h->nlat * 8, cudaMemcpyHostToDevice, s));
+    if (coslat && sinlat) {
+        CUX(cudaMemcpyAsync(arena + o_cl, coslat, (size_t)h->nlat * 8, cudaMemcpyHostToDevice, s));
+        CUX(cudaMemcpyAsync(arena + o_sl, sinlat, (size_t)h->nlat * 8, cudaMemcpyHostToDevice, s));
+    }
+    CUX(cudaMemcpyAsync(arena + o_slon, src_lon, (size_t)nsource * 8, cudaMemcpyHostToDevice, s));
+    CUX(cudaMemcpyAsync(arena + o_slat, src_lat, (size_t)nsource * 8, cudaMemcpyHostToDevice, s));
+    if (src_member) CUX(cudaMemcpyAsync(arena + o_mem, src_member, (size_t)nsource * 4, cudaMemcpyHostToDevice, s));
+    CUX(cudaMemcpyAsync(arena + o_zwn, zwn, (size_t)nzwn * 8, cudaMemcpyHostToDevice, s));
+    {
+        const int32_t *dmem = src_member ? (const int32_t *)(arena + o_mem) : nullptr;
+        rc = rwrt_bs_ready(h, (const float *)(arena + o_u), (const float *)(arena + o_v), (const double *)(arena + o_lon),
+                           (const double *)(arena + o_lat), (coslat && sinlat) ? (const double *)(arena + o_cl) : nullptr,
+                           (coslat && sinlat) ? (const double *)(arena + o_sl) : nullptr, nullptr, nullptr, s);
+        if (rc) goto done;
+        rc = rwrt_ray_init(h, nsource, (const double *)(arena + o_slon), (const double *)(arena + o_slat), dmem, nzwn,
+                           (const double *)(arena + o_zwn), freq, nt, (double *)(arena + o_out), s);
+        if (rc) goto done;
+        rc = rwrt_ray_run_rk45(h, nsource, dmem, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags,
+                               (double *)(arena + o_out), (int64_t *)(arena + o_acc), nullptr, (int8_t *)(arena + o_st),
+                               (int64_t *)(arena + o_tot), s);
+        if (rc) goto done;
+    }
+    CUX(cudaMemcpyAsync(out7_host, arena + o_out, nout * 8, cudaMemcpyDeviceToHost, s));
+    if (accepted_host) CUX(cudaMemcpyAsync(accepted_host, arena + o_acc, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
+    if (status_host) CUX(cudaMemcpyAsync(status_host, arena + o_st, (size_t)N, cudaMemcpyDeviceToHost, s));
+    if (total_accepted_host) CUX(cudaMemcpyAsync(total_accepted_host, arena + o_tot, 8, cudaMemcpyDeviceToHost, s));
+    CUX(cudaStreamSynchronize(s));
+done:
+    cudaFree(arena);
+    return rc;
+#undef CUX
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// rwrt_device.cuh -- device functions shared by the sampler, ray-init and RK45 kernels.
+//
+// Reference semantics being reproduced (file:line into yinan-codes/Rossby-wave-ray-tracing):
+//   interpolation.py:77-85, 103-135   index computation + bilinear blend (clamped indices)
+//   bs.py:513-519, 781-887            lon wrap, Mercator transform, |cos(lat)| <= 0.0175 mask
+//   wn.py:266-294                     group velocity ("extent" form)
+//   wr.py:44-82, 492-556              ray equations + |lat| >= pi/2, |l| >= 100 masks
+//
+// Layout: the 11 fields the ray equations consume (of the reference's 18) are packed per grid
+// point as 12 doubles = 96 B (u,v,ux,uy,vx,vy,qx,qy,qxx,qxy,qyy,pad), points ordered [i_lon][j_lat]
+// so the two latitude corners of a cell are 192 contiguous bytes.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rwrt {
+
+constexpr double PI = 3.14159265358979323846264338327950288419716939937510;  // constants.py:13
+constexpr double TWOPI = 2 * PI;
+constexpr double HALFPI = 0.5 * PI;
+constexpr double REARTH = 6.3712e6;                                           // constants.py:16
+constexpr double OMEGA = 7.2921e-5;                                           // constants.py:17
+constexpr double DELT = 1.0e-8;                                               // constants.py:28
+constexpr int NPK = 12;  // doubles per packed grid point
+
+struct Grid {
+    const double *fpk;     // (nmember, nlon_f, nlat, NPK)
+    size_t member_stride;  // doubles between members
+    int nlon_f, nlat;      // nlon_f = nlon + 1 when xcyclic (wrap column, bs.py:370-372)
+    double lon0, dlon, lat0, dlat;  // lon[0], lon[1]-lon[0], lat[0], lat[1]-lat[0] (interpolation.py:78-79)
+};
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// Python / numpy float remainder by 2*pi (result has the divisor's sign).  fmod is exact.
+__device__ __forceinline__ double pymod_2pi(double a)
+{
+    double m = fmod(a, TWOPI);
+    if (m != 0.0) {
+        if (m < 0.0) m += TWOPI;
+    } else {
+        m = 0.0;
+    }
+    return m;
+}
+
+// np.maximum: NaN if either operand is NaN
+__device__ __forceinline__ double np_maximum(double a, double b) { return (a != a || b != b) ? qnan() : fmax(a, b); }
+
+// Bilinear sample of the packed fields (interpolation.py:103-135).  f[0..10].
+__device__ __forceinline__ void sample_packed(const Grid &g, const double *__restrict__ fb, double lon, double lat,
+                                              double *f)
+{
+    double l1 = pymod_2pi(lon);  // bs.py:519
+    double l2 = pymod_2pi(l1);   // interpolation.py:80
+    double x = (l2 - g.lon0) / g.dlon;
+    double y = (lat - g.lat0) / g.dlat;
+    const int W = g.nlon_f, H = g.nlat;
+    int x0u = __double2int_rd(x), y0u = __double2int_rd(y);  // floor -> int32 (NaN -> 0 after the clamp either way)
+    int x0 = min(max(x0u, 0), W - 1), y0 = min(max(y0u, 0), H - 1);
+    int x1 = min(max(x0u + 1, 0), W - 1), y1 = min(max(y0u + 1, 0), H - 1);
+    double sx = x - (double)x0, sy = y - (double)y0;  // weights from the CLAMPED indices
+    double wa = (1 - sx) * sy, wb = sx * sy, wc = (1 - sx) * (1 - sy), wd = sx * (1 - sy);
+    const double2 *pa = reinterpret_cast<const double2 *>(fb + ((size_t)x0 * H + y1) * NPK);
+    const double2 *pb = reinterpret_cast<const double2 *>(fb + ((size_t)x1 * H + y1) * NPK);
+    const double2 *pc = reinterpret_cast<const double2 *>(fb + ((size_t)x0 * H + y0) * NPK);
+    const double2 *pd = reinterpret_cast<const double2 *>(fb + ((size_t)x1 * H + y0) * NPK);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double2 a = __ldg(pa + k), b = __ldg(pb + k), c = __ldg(pc + k), d = __ldg(pd + k);
+        f[2 * k] = a.x * wa + b.x * wb + c.x * wc + d.x * wd;
+        if (2 * k + 1 < 11) f[2 * k + 1] = a.y * wa + b.y * wb + c.y * wc + d.y * wd;
+    }
+}
+
+// Mercator quantities (bs.py:856-883).  Only what the ray path consumes.
+struct Merc {
+    double u, v, ux, uy, vx, vy, qx, qy, qxx, qxy, qyx, qyy;
+    double cosl, sinl;
+};
+
+__device__ __forceinline__ Merc sample_mercator(const Grid &g, const double *__restrict__ fb, double lon, double lat)
+{
+    Merc m;
+    if (!(fabs(lat) <= HALFPI)) {  // bs.py:787: rows outside +-pi/2 (or NaN) stay NaN
+        double n = qnan();
+        m.u = m.v = m.ux = m.uy = m.vx = m.vy = m.qx = m.qy = m.qxx = m.qxy = m.qyx = m.qyy = n;
+        m.cosl = cos(lat);
+        m.sinl = sin(lat);
+        return m;
+    }
+    double f[12];
+    sample_packed(g, fb, lon, lat, f);
+    double fu = f[0], fv = f[1], fux = f[2], fuy = f[3], fvx = f[4], fvy = f[5], fqx = f[6], fqy = f[7], fqxx = f[8],
+           fqxy = f[9], fqyy = f[10];
+    double cp = cos(lat), sp = sin(lat), tl = tan(lat);
+    m.cosl = cp;
+    m.sinl = sp;
+    double mask = (fabs(cp) <= 0.0175) ? 0.0 : 1.0;
+    cp = cp * mask + (1 - mask) * 1e-6;
+    m.qxx = fqxx * mask;
+    m.qyx = fqxy * cp * mask;
+    m.qxy = m.qyx * mask;
+    m.qyy = (fqyy * cp - fqy * sp) * cp * mask;
+    m.qx = fqx * mask;
+    m.qy = fqy * cp * mask;
+    m.ux = fux / cp * mask;
+    m.vx = fvx / cp * mask;
+    m.uy = (fuy + tl * fu) * mask;
+    m.vy = (fvy + tl * fv) * mask;
+    m.u = fu / cp * mask;
+    m.v = fv / cp * mask;
+    return m;
+}
+
+// wn.py:266-294
+__device__ __forceinline__ void ugvg_extent(double fu, double fv, double fqx, double fqy, double k, double l, double &ug,
+                                            double &vg)
+{
+    double kap = l / k;
+    double kap2 = kap * kap;
+    double kap1 = 1.0 + kap2;
+    double KK = k * k * kap1;
+    double den = KK * kap1;
+    ug = fu + (((1. - kap2) * fqy) - (2. * kap * fqx)) / den;
+    vg = fv + ((2. * kap * fqy) + ((1. - kap2) * fqx)) / den;
+}
+
+// wn.py:209-259 (t = 0 only)
+__device__ __forceinline__ void ugvg_numpy(double fu, double fv, double fqx, double fqy, double k, double l, double &ug,
+                                           double &vg)
+{
+    if (k == 0) { ug = 0; vg = 0; return; }
+    double nans = (l * 0) * (fu * fqx * fqy * 0) + 1;
+    if (nans != nans) nans = 0;
+    double kap1 = k * k - l * l;
+    double kap2 = 2 * k * l;
+    double KK2 = k * k + l * l;
+    double kk4 = KK2 * KK2;
+    ug = (fu + (kap1 * fqy - kap2 * fqx) / kk4) * nans;
+    vg = (fv + (kap1 * fqx + kap2 * fqy) / kk4) * nans;
+}
+
+// One right-hand side: wr.py:784-789 -> 492-556 -> 44-82.  y = (lon, lat, k, l, A).
+__device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict__ fb, const double *y, double *dy)
+{
+    double lon = y[0], lat = y[1], kx = y[2], ky = y[3], amp = y[4];
+    bool err = (fabs(lat) >= HALFPI) || (fabs(ky) >= 100.0);  // wr.py:508-510
+    if (err) {
+        double n = qnan();
+        dy[0] = dy[1] = dy[2] = dy[3] = dy[4] = n;  // wr.py:552-553
+        return;
+    }
+    Merc m = sample_mercator(g, fb, lon, lat);
+    double ug, vg;
+    ugvg_extent(m.u, m.v, m.qx, m.qy, kx, ky, ug, vg);
+    double kap = ky / kx;
+    double kap2 = kap * kap;
+    double kap1 = 1 + kap * kap;
+    double kk = kx * kx * kap1;
+    double dzwn = -kx * ((m.ux + kap * m.vx) + (kap * m.qxx - m.qyx) / kk);
+    double dmwn = -kx * ((m.uy + kap * m.vy) + (kap * m.qxy - m.qyy) / kk);
+    double damp1 = 2.0 * (m.ux + m.vy + kap * (m.vx + m.uy)) / kap1;
+    double damp2 = 2.0 * (kap * (m.qxx - m.qyy) + (kap2 - 1.0) * m.qxy) / (kk * kap1);
+    double damp3 = -2.0 * m.sinl * m.v;
+    double damp = damp1 + damp2 + damp3;
+    dy[0] = ug / REARTH;
+    dy[1] = (vg * m.cosl) / REARTH;
+    dy[2] = dzwn / REARTH;
+    dy[3] = dmwn / REARTH;
+    dy[4] = (damp * amp) / REARTH;
+}
+
+// wr.py:97-112
+__device__ __forceinline__ double haversine(double lon_c, double lat_c, double lon_p, double lat_p)
+{
+    double dlon = lon_c - lon_p, dlat = lat_c - lat_p;
+    double s1 = sin(dlat / 2.0), s2 = sin(dlon / 2.0);
+    double a = s1 * s1 + cos(lat_p) * cos(lat_c) * (s2 * s2);
+    double c = 2 * atan2(sqrt(a), sqrt(1.0 - a));
+    return fabs(c);
+}
+
+}  // namespace rwrt

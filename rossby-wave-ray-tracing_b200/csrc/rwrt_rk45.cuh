@@ -1,0 +1,324 @@
+// rwrt_rk45.cuh -- the hot kernels: Dormand-Prince 5(4) with the reference's step controller,
+// one ray per lane, lanes advance through output intervals independently and refill from a
+// global queue when their ray finishes or dies (compaction of finished rays at warp granularity).
+//
+// This header is compiled twice (rwrt_rk45_fast.cu: FMA contraction on; rwrt_rk45_strict.cu:
+// -fmad=false, every operation a separate IEEE op in the reference's order).  RWRT_VARIANT names
+// the namespace so both sets of kernels live in one library.
+//
+// Reference semantics (file:line): rkf45.py:34-99 (initial step), 222-253 (step), 259-321
+// (rk_step), 375-514 (_step_impl: clamp once per pass, retry loop, NaN-as-accept, controller),
+// 601-615 (tableau); wr.py:767-887 (output-interval loop, pole / speed cut-offs, ug/vg at outputs).
+#pragma once
+#include "rwrt_device.cuh"
+#include "rwrt_rk45_params.h"
+
+#ifndef RWRT_VARIANT
+#error "define RWRT_VARIANT (fast | strict)"
+#endif
+
+namespace rwrt {
+
+namespace RWRT_VARIANT {
+
+// rkf45.py:604-615
+#define A21 (1.0 / 5)
+#define A31 (3.0 / 40)
+#define A32 (9.0 / 40)
+#define A41 (44.0 / 45)
+#define A42 (-56.0 / 15)
+#define A43 (32.0 / 9)
+#define A51 (19372.0 / 6561)
+#define A52 (-25360.0 / 2187)
+#define A53 (64448.0 / 6561)
+#define A54 (-212.0 / 729)
+#define A61 (9017.0 / 3168)
+#define A62 (-355.0 / 33)
+#define A63 (46732.0 / 5247)
+#define A64 (49.0 / 176)
+#define A65 (-5103.0 / 18656)
+#define B1 (35.0 / 384)
+#define B2 0.0
+#define B3 (500.0 / 1113)
+#define B4 (125.0 / 192)
+#define B5 (-2187.0 / 6784)
+#define B6 (11.0 / 84)
+#define E1 (-71.0 / 57600)
+#define E2 0.0
+#define E3 (71.0 / 16695)
+#define E4 (-71.0 / 1920)
+#define E5 (17253.0 / 339200)
+#define E6 (-22.0 / 525)
+#define E7 (1.0 / 40)
+
+__device__ __forceinline__ const double *member_base(const RunParams &p, long long slot)
+{
+    if (p.src_member == nullptr) return p.g.fpk;
+    int isrc = (int)((slot / p.nzwn) % p.nsource);
+    return p.g.fpk + (size_t)p.src_member[isrc] * p.g.member_stride;
+}
+
+// rkf45.py:29-31: squares summed component by component, sqrt, / sqrt(5)
+__device__ __forceinline__ double rms5(double a0, double a1, double a2, double a3, double a4)
+{
+    double s = a0 * a0;
+    s = s + a1 * a1;
+    s = s + a2 * a2;
+    s = s + a3 * a3;
+    s = s + a4 * a4;
+    return sqrt(s) / sqrt(5.0);
+}
+
+// rkf45.py:34-99 select_initial_step (direction +1, error-estimator order 4)
+__device__ double initial_step(const Grid &g, const double *fb, const double *y0, const double *f0, double rtol,
+                               double atol)
+{
+    double scale[5], y1[5], f1[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) scale[c] = atol + fabs(y0[c]) * rtol;
+    double d0 = rms5(y0[0] / scale[0], y0[1] / scale[1], y0[2] / scale[2], y0[3] / scale[3], y0[4] / scale[4]);
+    double d1 = rms5(f0[0] / scale[0], f0[1] / scale[1], f0[2] / scale[2], f0[3] / scale[3], f0[4] / scale[4]);
+    double h0 = 0.01 * d0 / d1;
+    if (d0 < 1e-5) h0 = 1e-6;
+    if (d1 < 1e-5) h0 = 1e-6;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) y1[c] = y0[c] + h0 * 1.0 * f0[c];
+    ray_rhs(g, fb, y1, f1);
+    double d2 = rms5((f1[0] - f0[0]) / scale[0], (f1[1] - f0[1]) / scale[1], (f1[2] - f0[2]) / scale[2],
+                     (f1[3] - f0[3]) / scale[3], (f1[4] - f0[4]) / scale[4]) / h0;
+    bool m1 = !(d1 > 1e-15), m2 = !(d2 > 1e-15);
+    double mx = (d1 != d1) ? d2 : ((d2 != d2) ? d1 : fmax(d1, d2));  // np.nanmax
+    double h1 = pow(0.01 / mx, 1.0 / (4 + 1));
+    if (m1 && m2) h1 = np_maximum(1e-6, h0 * 1e-3);
+    double hh = 100 * h0;
+    if (hh != hh || h1 != h1) return qnan();  // np.min propagates NaN
+    return hh < h1 ? hh : h1;
+}
+
+// Prepare: per live ray f0 = fun(y0) (rkf45.py:345) and the initial step (rkf45.py:347-349).
+__global__ void __launch_bounds__(128) rk45_prepare(RunParams p)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.nlive) return;
+    long long slot = p.live[i];
+    const size_t pl = (size_t)p.nt * p.N;
+    double y[5], f[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) y[c] = p.out[c * pl + slot];
+    const double *fb = member_base(p, slot);
+    ray_rhs(p.g, fb, y, f);
+    double h = initial_step(p.g, fb, y, f, p.rtol, p.atol);
+    double *st = p.state + (size_t)i * 12;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) { st[c] = y[c]; st[5 + c] = f[c]; }
+    st[10] = h;
+    st[11] = 0.0;
+}
+
+// NaN-root slots: rlon, rlat, rzwn keep their t=0 value at every output
+// time, the other four planes are NaN; their step count is zero.
+__global__ void __launch_bounds__(256) fill_static_slots(RunParams p)
+{
+    long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int it = blockIdx.y + 1;
+    if (slot >= p.N || it >= p.nt) return;
+    const size_t pl = (size_t)p.nt * p.N;
+    double s = p.out[0 * pl + slot] + p.out[1 * pl + slot] + p.out[2 * pl + slot] + p.out[3 * pl + slot] +
+               p.out[4 * pl + slot];
+    if (s == s) return;  // live slot: written by the integrator
+    size_t o = (size_t)it * p.N + slot;
+    double n = qnan();
+    // rays whose lon/lat/k are themselves NaN propagate that NaN; reference does the same
+    p.out[0 * pl + o] = p.out[0 * pl + slot];
+    p.out[1 * pl + o] = p.out[1 * pl + slot];
+    p.out[2 * pl + o] = p.out[2 * pl + slot];
+    p.out[3 * pl + o] = p.out[3 * pl + slot];  // NaN root stays NaN; a finite l with NaN A stays as it is
+    p.out[4 * pl + o] = p.out[4 * pl + slot];
+    // ug, vg at outputs: fresh sample + extent form (wr.py:856-865); NaN because l or the state is NaN
+    p.out[5 * pl + o] = n;
+    p.out[6 * pl + o] = n;
+    if (it == 1) {
+        if (p.accepted) p.accepted[slot] = 0;
+        if (p.attempts) p.attempts[slot] = 0;
+        if (p.status) p.status[slot] = 0;
+    }
+}
+
+struct Lane {
+    double y[5], f[5];
+    double t, h_abs, plon, plat;
+    long long slot;
+    long long acc, att;
+    int it;         // next output row to produce
+    bool rejected;  // a rejection happened since the last accepted step (rkf45.py:462-469)
+    bool fresh;     // next attempt is the first of a pass: apply the min-step clamp (rkf45.py:383-387)
+};
+
+__device__ __forceinline__ void write_row(const RunParams &p, long long slot, int it, double lon, double lat, double k,
+                                          double l, double a, double ug, double vg)
+{
+    const size_t pl = (size_t)p.nt * p.N;
+    size_t o = (size_t)it * p.N + slot;
+    p.out[0 * pl + o] = lon;
+    p.out[1 * pl + o] = lat;
+    p.out[2 * pl + o] = k;
+    p.out[3 * pl + o] = l;
+    p.out[4 * pl + o] = a;
+    p.out[5 * pl + o] = ug;
+    p.out[6 * pl + o] = vg;
+}
+
+// The integrator.  Persistent grid; every lane owns one ray at a time.
+__global__ void __launch_bounds__(128) rk45_integrate(RunParams p)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane_id = threadIdx.x & 31;
+    Lane L;
+    L.slot = -1;
+    const double *fb = p.g.fpk;
+    bool queue_empty = false;
+    long long my_total = 0;
+
+    for (;;) {
+        __syncwarp();
+        // ---- refill idle lanes from the queue (one atomic per warp) ----
+        bool idle = (L.slot < 0);
+        unsigned idle_mask = __ballot_sync(FULL, idle);
+        if (idle_mask == FULL && queue_empty) break;
+        if (idle_mask != 0 && !queue_empty) {
+            int leader = __ffs(idle_mask) - 1;
+            unsigned long long base = 0;
+            if (lane_id == leader) base = atomicAdd(p.queue, (unsigned long long)__popc(idle_mask));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= (unsigned long long)p.nlive) queue_empty = true;
+            if (idle) {
+                unsigned long long mine = base + __popc(idle_mask & ((1u << lane_id) - 1));
+                if (mine < (unsigned long long)p.nlive) {
+                    const double *st = p.state + (size_t)mine * 12;
+                    L.slot = p.live[mine];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) { L.y[c] = st[c]; L.f[c] = st[5 + c]; }
+                    L.h_abs = st[10];
+                    L.t = 0.0;
+                    L.plon = L.y[0];
+                    L.plat = L.y[1];
+                    L.acc = 0;
+                    L.att = 0;
+                    L.it = 1;
+                    L.rejected = false;
+                    L.fresh = true;
+                    fb = member_base(p, L.slot);
+                }
+            }
+        }
+        if (L.slot < 0) continue;
+
+        // ---- one attempt (rkf45.py:410-502) ----
+        double tb = L.it * p.tstep;  // wr.py:798-801
+        if (L.it == p.nt - 1 && tb > p.ttotal) tb = p.ttotal;
+        if (L.fresh) {  // rkf45.py:383-387, once per pass
+            if (!(L.h_abs >= p.gmin) && L.h_abs == L.h_abs) L.h_abs = p.gmin;
+            L.rejected = false;
+            L.fresh = false;
+        }
+        double t_new = L.t + L.h_abs;  // rkf45.py:426-435
+        if (t_new - tb > 0) t_new = tb;
+        double h = t_new - L.t;
+        double h_abs = fabs(h);
+        ++L.att;
+        double k2[5], k3[5], k4[5], k5[5], k6[5], k7[5], ys[5], yn[5];
+        const double *k1 = L.f;
+        // rkf45.py:306-311: dy = (sum_j K_j a_sj) * h, accumulated in j order
+#pragma unroll
+        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * A21) * h;
+        ray_rhs(p.g, fb, ys, k2);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * A31 + k2[c] * A32) * h;
+        ray_rhs(p.g, fb, ys, k3);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * A41 + k2[c] * A42 + k3[c] * A43) * h;
+        ray_rhs(p.g, fb, ys, k4);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * A51 + k2[c] * A52 + k3[c] * A53 + k4[c] * A54) * h;
+        ray_rhs(p.g, fb, ys, k5);
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+            ys[c] = L.y[c] + (k1[c] * A61 + k2[c] * A62 + k3[c] * A63 + k4[c] * A64 + k5[c] * A65) * h;
+        ray_rhs(p.g, fb, ys, k6);
+#pragma unroll
+        for (int c = 0; c < 5; ++c)  // rkf45.py:316 (the zero B2 term is part of the einsum)
+            yn[c] = L.y[c] + h * (k1[c] * B1 + k2[c] * B2 + k3[c] * B3 + k4[c] * B4 + k5[c] * B5 + k6[c] * B6);
+        ray_rhs(p.g, fb, yn, k7);  // rkf45.py:317-319
+        double r[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {  // rkf45.py:442-446
+            double scale = p.atol + np_maximum(fabs(L.y[c]), fabs(yn[c])) * p.rtol;
+            double e = k1[c] * E1 + k2[c] * E2 + k3[c] * E3 + k4[c] * E4 + k5[c] * E5 + k6[c] * E6 + k7[c] * E7;
+            r[c] = (h * e) / scale;
+        }
+        double err = rms5(r[0], r[1], r[2], r[3], r[4]);
+        if (err != err) err = 0;
+        bool accept = err < 1;
+        double factor = 0.9 * pow(err, -0.2);
+        if (accept) {  // rkf45.py:449-471
+            if (!(factor < 10)) factor = 10;
+            if (err == 0) factor = 10;
+            if (L.rejected && factor > 1.0) factor = 1.0;
+        } else {  // rkf45.py:474-479
+            if (!(factor > 0.2)) factor = 0.2;
+            L.rejected = true;
+        }
+        L.h_abs = h_abs * factor;
+        if (!accept) continue;
+
+        // ---- accepted step ----
+        ++L.acc;
+        L.t = (t_new != t_new) ? tb : t_new;  // rkf45.py:503
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { L.y[c] = yn[c]; L.f[c] = k7[c]; }
+        L.fresh = true;
+        double ysum = L.y[0] + L.y[1] + L.y[2] + L.y[3] + L.y[4];  // np.mean(y) is NaN (rkf45.py:400-402)
+        bool dead = (ysum != ysum);
+        if (!dead && L.t != tb) continue;
+
+        // ---- output time reached (wr.py:831-885) ----
+        int code = 1;  // RWRT_RAY_ALIVE
+        if (dead) code = 4;
+        if (fabs(L.y[1]) >= HALFPI) {  // wr.py:838-843
+            dead = true;
+            code = 2;
+        }
+        if (!dead) {
+            double dd = haversine(L.y[0], L.y[1], L.plon, L.plat);  // wr.py:844-850
+            if (fabs(dd) >= p.cut) {
+                dead = true;
+                code = 3;
+            }
+        }
+        if (dead) {
+            double n = qnan();
+            for (int it = L.it; it < p.nt; ++it) write_row(p, L.slot, it, n, n, n, n, n, n, n);
+        } else {
+            Merc m = sample_mercator(p.g, fb, L.y[0], L.y[1]);  // wr.py:856-865
+            double ug, vg;
+            ugvg_extent(m.u, m.v, m.qx, m.qy, L.y[2], L.y[3], ug, vg);
+            write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
+            L.plon = L.y[0];
+            L.plat = L.y[1];
+            ++L.it;
+        }
+        if (dead || L.it >= p.nt) {  // ray finished: publish counters, free the lane
+            if (p.accepted) p.accepted[L.slot] = L.acc;
+            if (p.attempts) p.attempts[L.slot] = L.att;
+            if (p.status) p.status[L.slot] = (signed char)code;
+            my_total += L.acc;
+            L.slot = -1;
+        }
+    }
+    // block-level reduction of the accepted-step total (the metric), one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) my_total += __shfl_down_sync(FULL, my_total, o);
+    if (lane_id == 0 && my_total) atomicAdd(p.total_accepted, (unsigned long long)my_total);
+}
+
+}  // namespace RWRT_VARIANT
+}  // namespace rwrt

@@ -1,0 +1,35 @@
+// Fast build of the RK45 kernels: default nvcc floating-point contraction (FMA) on.
+#define RWRT_VARIANT fast
+#include "rwrt_rk45.cuh"
+#include "rwrt_internal.h"
+
+namespace rwrt {
+void launch_rk45_fast(const RunParams &p, int prepare_blocks, int fill_blocks, int integrate_blocks, cudaStream_t s)
+{
+    if (p.N > 0 && p.nt > 1) fast::fill_static_slots<<<dim3(fill_blocks, p.nt - 1), 256, 0, s>>>(p);
+    if (p.nlive > 0) {
+        fast::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
+        fast::rk45_integrate<<<integrate_blocks, 128, 0, s>>>(p);
+    }
+}
+int occupancy_rk45_fast()
+{
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast::rk45_integrate, 128, 0);
+    return nb;
+}
+__global__ void rhs_kernel_fast(Grid g, long long n, const double *y, const int32_t *member, double *dy)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double yy[5], d[5];
+    for (int c = 0; c < 5; ++c) yy[c] = y[c * n + i];
+    const double *fb = g.fpk + (member ? (size_t)member[i] * g.member_stride : 0);
+    ray_rhs(g, fb, yy, d);
+    for (int c = 0; c < 5; ++c) dy[c * n + i] = d[c];
+}
+void launch_rhs_fast(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s)
+{
+    if (n > 0) rhs_kernel_fast<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, n, y, member, dy);
+}
+}  // namespace rwrt

@@ -1,0 +1,24 @@
+// rwrt_rk45_params.h -- kernel parameter block of the RK45 kernels (shared by both builds and the API).
+#pragma once
+#include "rwrt_device.cuh"
+
+namespace rwrt {
+
+struct RunParams {
+    Grid g;
+    const int32_t *src_member;  // (nsource) or nullptr
+    int nsource, nzwn, nt;
+    long long N;                // slots = 3 * nsource * nzwn
+    double tstep, ttotal, rtol, atol, gmin, cut;
+    double *out;                // 7 planes, each (nt, N)
+    const int32_t *live;        // compacted list of live slots
+    long long nlive;
+    double *state;              // (nlive, 12): y[5], f[5], h_abs, pad
+    long long *accepted;        // (N) or nullptr
+    long long *attempts;        // (N) or nullptr
+    signed char *status;        // (N) or nullptr
+    unsigned long long *queue;  // work-fetch counter
+    unsigned long long *total_accepted;
+};
+
+}  // namespace rwrt

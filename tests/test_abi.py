@@ -1,0 +1,103 @@
+"""CPU tests of the boundary: the C-ABI library builds, loads and exports every symbol that
+include/rwrt.h declares; the facade mirrors the reference's interface and error behaviour and fails
+loudly (no CPU fallback) when no GPU is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rwrt_b200  # noqa: F401
+from rwrt_b200 import build as rbuild
+from rwrt_b200 import lib
+from rwrt_b200.wr import WR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    rbuild.build()
+    return lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "rwrt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rwrt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(L):
+    syms = header_symbols()
+    assert set(syms) == set(lib.SYMBOLS)
+    for s in syms:
+        assert hasattr(L, s), s
+    assert L.rwrt_abi_version() == 1
+
+
+def test_no_compute_without_gpu(L):
+    if lib.device_count() > 0:
+        pytest.skip("GPU present")
+    h = lib.vp()
+    rc = L.rwrt_create(0, 144, 73, 1, 1, C.byref(h))
+    assert rc == -2 and b"no CPU fallback" in L.rwrt_last_error()
+    w = WR(3, 1, 7200.0, 86400.0, nx=144, ny=73)
+    with pytest.raises(lib.RwrtError):
+        w.bs.ready(xcyclic=True)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "rossby-wave-ray-tracing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.replace("oracle/gridding.py", "").replace("checker is oracle", "") or \
+                    f in ("rwrt_grid.cu",), f"{f} mentions the oracle"
+
+
+def test_wr_host_logic_matches_reference_semantics():
+    w = WR(3, 6, 2 * 3600.0, 30 * 86400.0, nx=144, ny=73)
+    assert w.nt == 361                                   # wr.py:157
+    assert w.cut_off[0] == 0.1 * 7200.0 / 3600.0         # wr.py:170
+    with pytest.raises(ValueError):
+        w.set_zwn([1.0, 2.0])                            # wr.py:216-217
+    with pytest.raises(ValueError):
+        w.set_source_array([1.0], [2.0])                 # wr.py:229-230
+    with pytest.raises(ValueError):
+        w.set_source_matrix(0.0, 0.0, 1, 1, 2, 2)        # wr.py:242-243
+    with pytest.raises(ValueError):
+        w.set_source_matrix(0.0, 80.0, 1, 10, 3, 2)      # wr.py:245-246
+    w.set_source_matrix(350.0, -4.0, 4, 2, 3, 2)
+    # the reference's double loop (wr.py:249-258), restated
+    exp_lon, exp_lat = [], []
+    for iy in range(2):
+        for ix in range(3):
+            exp_lon.append(((350.0 % 360.0 + ix * 4) % 360.0) * (np.pi / 180.0))
+            exp_lat.append((-4.0 + iy * 2) * (np.pi / 180.0))
+    assert np.array_equal(w.source_lon, np.array(exp_lon)) and np.array_equal(w.source_lat, np.array(exp_lat))
+    assert w.rlon.shape == (361, 3, 6, 3) and np.isnan(w.rlon).all()   # wr.py:160-167
+    with pytest.raises(ValueError):
+        WR(3, 1)                                          # wr.py:139-141: nx/ny or ncfile needed
+
+
+def test_ray_run_rejects_non_gpu_paths():
+    w = WR(1, 1, 7200.0, 86400.0, nx=144, ny=73)
+    for kw in (dict(mode="original"), dict(mode="numpy", inte_method=""), dict(mode="numpy", inte_method="rk4")):
+        with pytest.raises(NotImplementedError):
+            w.ray_run(**kw)
+
+
+def test_ncio_roundtrip(tmp_path):
+    from rwrt_b200 import ncio, synthetic
+    u, v = synthetic.jet_z()
+    lat_deg = np.linspace(90, -90, 73).astype("float32")       # descending: must be flipped (bs.py:251-256)
+    lon_deg = (np.arange(144) * 2.5).astype("float32")
+    p = str(tmp_path / "uv.npz")
+    np.savez(p, u=u.T[::-1], v=v.T[::-1], lat=lat_deg, lon=lon_deg)
+    d = ncio.read_uv(p, 144, 73)
+    assert np.array_equal(d["u"], u) and np.array_equal(d["v"], v)
+    assert ncio.grid_shape(p) == (73, 144)
+    # coordinates carry float32 precision (bs.py:222-236)
+    assert np.array_equal(d["lon"], (lon_deg * np.pi / 180).astype("float64"))

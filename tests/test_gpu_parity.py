@@ -1,0 +1,264 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI
+(`librwrt.so` via the ctypes facade), against the golden fixtures made from the unmodified
+reference and against the C oracle on the same seeded inputs."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import parity
+import rwrt_b200  # noqa: F401
+from rwrt_b200 import lib, synthetic
+from rwrt_b200.wr import WR
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def make_wr(u, v, zwn, slon_rad, slat_rad, days, freq=0.0, tstep_h=2.0, **kw):
+    nlon, nlat = u.shape
+    w = WR(len(zwn), len(slon_rad), tstep_h * 3600.0, days * 86400.0, freq, nx=nlon, ny=nlat, **kw)
+    w.bs.lon, w.bs.lat = synthetic.grid_coords(nlon, nlat)
+    w.bs.u, w.bs.v = u, v
+    w.bs.ready(xcyclic=True)
+    w.set_zwn(zwn)
+    w.source_lon = np.asarray(slon_rad, dtype=np.float64)
+    w.source_lat = np.asarray(slat_rad, dtype=np.float64)
+    return w
+
+
+FIELD_CASES = {"jet_g1": ("jet_z", {}), "gc_g1": ("great_circle", {}),
+               "clim_g1": ("clim", dict(nlon=144, nlat=73)), "clim_g2": ("clim", dict(nlon=360, nlat=181))}
+
+
+@pytest.mark.parametrize("tag", list(FIELD_CASES))
+def test_bs_ready_bit_exact(tag):
+    """K1 vs bs.py:318-407: all 18 stacked fields and 9 diagnostic planes bit-identical."""
+    g = parity.load("fields")
+    fn, kw = FIELD_CASES[tag]
+    u, v = getattr(synthetic, fn)(**kw)
+    w = make_wr(u, v, [1.0], [0.1], [0.1], 1.0)
+    assert w.bs.fields.shape == tuple(g[tag + "_fields_shape"])
+    np.testing.assert_array_equal(w.bs.fields.reshape(-1)[g[tag + "_sample_idx"]], g[tag + "_sample_val"])
+    assert sha(w.bs.fields) == str(g[tag + "_fields_sha"])
+    for nm in ("q", "uxx", "uyy", "vxx", "vyy", "uxy", "vxy", "betam", "KS"):
+        assert sha(getattr(w.bs, nm)) == str(g[f"{tag}_{nm}_sha"]), nm
+
+
+def test_bs_ready_device_trig_tables():
+    """coslat/sinlat = NULL: tables computed on the device; fields agree with the oracle to 1e-12."""
+    import torch
+    u, v = synthetic.clim(144, 73)
+    lon, lat = synthetic.grid_coords(144, 73)
+    L = lib.load()
+    h = lib.vp()
+    lib.check(L.rwrt_create(0, 144, 73, 1, 1, C.byref(h)))
+    du, dv = torch.from_numpy(u).cuda(), torch.from_numpy(v).cuda()
+    dlon, dlat = torch.from_numpy(lon).cuda(), torch.from_numpy(lat).cuda()
+    f18 = torch.empty((145, 73, 18), dtype=torch.float64, device="cuda")
+    lib.check(L.rwrt_bs_ready(h, lib.ptr(du), lib.ptr(dv), lib.ptr(dlon), lib.ptr(dlat), None, None, lib.ptr(f18),
+                              None, lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = oracle.bs_ready(u, v, lat, True)
+    got = f18.cpu().numpy()
+    assert np.max(np.abs(got - ref) / (np.abs(ref) + 1e-30)) < 1e-9
+    L.rwrt_destroy(h)
+
+
+def test_sampler_rhs_vs_reference():
+    """rwrt_sample_mercator / rwrt_rhs vs bs.py:781-887 and wr.py:492-556 outputs of the reference."""
+    import torch
+    g = parity.load("pointwise")
+    u, v = synthetic.clim(144, 73)
+    w = make_wr(u, v, [1.0], [0.1], [0.1], 1.0)
+    got = w.bs.cal_bs_mercator_point(g["plon"], g["plat"], mode="numpy")[:12].T
+    ref = g["merc"]
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = np.isfinite(ref)
+    assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-6)) < 1e-11
+    y = torch.from_numpy(np.ascontiguousarray(g["y"].T)).cuda()       # (5, n)
+    for flags in (lib.MODE_FAST, lib.MODE_STRICT):
+        dy = torch.empty_like(y)
+        lib.check(lib.load().rwrt_rhs(w.bs._h, y.shape[1], lib.ptr(y), None, lib.ptr(dy), flags, lib.stream_ptr()))
+        got = dy.cpu().numpy().T
+        ref = g["dy"]
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = np.isfinite(ref)
+        assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-12)) < 1e-9
+    # and against the oracle, tighter (same libm class)
+    orc = oracle.rhs(oracle.bs_ready(u, v, w.bs.lat, True), w.bs.lon, w.bs.lat, g["y"])
+    ok = np.isfinite(orc)
+    assert np.max(np.abs(got[ok] - orc[ok]) / np.maximum(np.abs(orc[ok]), 1e-12)) < 1e-10
+
+
+TRAJ = ["c1_jet", "great_circle", "clim_g1", "clim_g1_freq", "clim_g2"]
+
+
+def run_gpu(g, strict):
+    u, v = parity.background(g)
+    w = make_wr(u, v, g["zwn"], g["src_lon_rad"], g["src_lat_rad"], float(g["days"]), float(g["freq"]),
+                float(g["tstep_h"]), rtol=float(g["rtol"]), atol=float(g["atol"]),
+                MinStepFactor=float(g["min_step_factor"]))
+    assert sha(w.bs.fields) == str(g["fields_sha"])
+    w.ray_run(mode="numpy", root_method="numpy", inte_method="rk45", strict=strict)
+    return w
+
+
+@pytest.mark.parametrize("name", TRAJ)
+def test_initial_state_vs_reference(name):
+    """K2 vs wr.py:344-395: slot layout identical everywhere; values bit-identical."""
+    g = parity.load(name)
+    w = run_gpu(g, strict=True)
+    for n in parity.NAMES:
+        got, ref = getattr(w, n)[0], g[n][0]
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), n
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=0, equal_nan=True, err_msg=n)
+    exact = np.mean([(getattr(w, n)[0] == g[n][0])[np.isfinite(g[n][0])].mean() for n in ("rmwn", "rug", "rvg")])
+    assert exact > 0.98
+
+
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+@pytest.mark.parametrize("name", TRAJ)
+def test_trajectories_vs_reference(name, strict):
+    """K3 vs wr.py:767-887 on the reference's own outputs: < 1e-6 deg, equal step counts (non-grazing)."""
+    g = parity.load(name)
+    w = run_gpu(g, strict)
+    got = {n: getattr(w, n) for n in parity.NAMES}
+    ref = {n: g[n] for n in parity.NAMES}
+    st = parity.compare(got, w.accepted, ref, g["accepted"], g["nongrazing"], f"{name}/{'strict' if strict else 'fast'}")
+    assert w.total_accepted == int(w.accepted.sum())
+    live = ~np.isnan(g["rmwn"][0])
+    assert (w.status[~live] == lib.RAY_NO_ROOT).all() and (w.status[live] != lib.RAY_NO_ROOT).all()
+    print(name, st)
+
+
+def oracle_run(u, v, slon, slat, zwn, days, freq=0.0):
+    lon, lat = synthetic.grid_coords(*u.shape)
+    F = oracle.bs_ready(u, v, lat, True)
+    nt = int(days * 86400.0 / 7200.0) + 1
+    out = oracle.ray_init(F, lon, lat, slon, slat, zwn, freq, nt)
+    acc, _ = oracle.ray_run_rk45(F, lon, lat, out, 7200.0, days * 86400.0)
+    return {n: out[k] for k, n in enumerate(parity.NAMES)}, acc
+
+
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+def test_vs_oracle_medium(strict):
+    """1-degree Clim, 600 seeded sources x k=1..6, 10 days: CUDA vs the C oracle on the same inputs;
+    the non-grazing set comes from two oracle runs (sources moved by one ulp)."""
+    u, v = synthetic.clim(360, 181)
+    sl, sa = synthetic.random_sources(600, 99)
+    slon, slat = np.radians(sl), np.radians(sa)
+    zwn = np.arange(1.0, 7.0)
+    ref, acc = oracle_run(u, v, slon, slat, zwn, 10.0)
+    per, acc_p = oracle_run(u, v, np.nextafter(slon, np.inf), slat, zwn, 10.0)
+    ng = np.ones(acc.shape, bool)
+    for n in parity.NAMES:
+        ng &= np.all(np.isnan(ref[n]) == np.isnan(per[n]), axis=0)
+    for n in ("rlon", "rlat"):
+        with np.errstate(invalid="ignore"):
+            d = np.abs(ref[n] - per[n])
+        ng &= np.degrees(np.where(np.isnan(d), 0, d).max(axis=0)) < 1e-7
+    ng &= acc == acc_p
+    w = make_wr(u, v, zwn, slon, slat, 10.0)
+    w.ray_run(mode="numpy", root_method="numpy", inte_method="rk45", strict=strict)
+    got = {n: getattr(w, n) for n in parity.NAMES}
+    st = parity.compare(got, w.accepted, ref, acc, ng, "medium")
+    print(st)
+    assert st["nongrazing"] > 0.8 * st["live"]
+    # whole-batch sanity: total accepted steps within 0.5 % of the oracle's even counting grazing rays
+    assert abs(st["steps_total"] - st["steps_total_ref"]) < 5e-3 * st["steps_total_ref"]
+
+
+def test_batch_composition_independence():
+    """A ray's result does not depend on which other rays share its batch (SURVEY.md probe9):
+    running a slice of the sources alone reproduces the same bits -- what makes source sharding exact."""
+    u, v = synthetic.clim(360, 181)
+    sl, sa = synthetic.random_sources(300, 5)
+    slon, slat = np.radians(sl), np.radians(sa)
+    zwn = np.array([1.0, 3.0, 5.0])
+    w = make_wr(u, v, zwn, slon, slat, 8.0)
+    w.ray_run(mode="numpy", inte_method="rk45")
+    w2 = make_wr(u, v, zwn, slon[100:180], slat[100:180], 8.0)
+    w2.ray_run(mode="numpy", inte_method="rk45")
+    for n in parity.NAMES:
+        assert np.array_equal(getattr(w, n)[:, :, 100:180, :], getattr(w2, n), equal_nan=True), n
+    assert np.array_equal(w.accepted[:, 100:180, :], w2.accepted)
+    # idempotence: running again reproduces the same bits (no order-dependent state in the engine)
+    first = {n: getattr(w, n).copy() for n in parity.NAMES}
+    w.ray_run(mode="numpy", inte_method="rk45")
+    for n in parity.NAMES:
+        assert np.array_equal(first[n], getattr(w, n), equal_nan=True), n
+
+
+def test_c_abi_host_entry_equals_facade():
+    """rwrt_real2d_host (host pointers, H2D/D2H inside) returns what the facade returns."""
+    u, v = synthetic.clim(144, 73)
+    sl, sa = synthetic.random_sources(50, 3)
+    slon, slat = np.radians(sl), np.radians(sa)
+    zwn = np.array([1.0, 2.0, 4.0])
+    days = 5.0
+    w = make_wr(u, v, zwn, slon, slat, days)
+    w.ray_run(mode="numpy", inte_method="rk45")
+    lon, lat = synthetic.grid_coords(144, 73)
+    L = lib.load()
+    h = lib.vp()
+    lib.check(L.rwrt_create(0, 144, 73, 1, 1, C.byref(h)))
+    nt = w.nt
+    out = np.empty((7, nt, 3, 50, 3))
+    acc = np.empty(3 * 50 * 3, dtype=np.int64)
+    status = np.empty(3 * 50 * 3, dtype=np.int8)
+    total = np.zeros(1, dtype=np.int64)
+    cl, sn = np.cos(lat), np.sin(lat)
+    lib.check(L.rwrt_real2d_host(h, lib.ptr(u), lib.ptr(v), lib.ptr(lon), lib.ptr(lat), lib.ptr(cl), lib.ptr(sn), 50,
+                                 lib.ptr(slon), lib.ptr(slat), None, 3, lib.ptr(zwn), 0.0, nt, 7200.0, days * 86400.0,
+                                 1e-6, 1e-6, 1e-3, 0.1, lib.MODE_FAST, lib.ptr(out), lib.ptr(acc), lib.ptr(status),
+                                 lib.ptr(total), None), "rwrt_real2d_host")
+    for k, n in enumerate(parity.NAMES):
+        assert np.array_equal(out[k], getattr(w, n), equal_nan=True), n
+    assert np.array_equal(acc.reshape(3, 50, 3), w.accepted) and int(total[0]) == w.total_accepted
+    L.rwrt_destroy(h)
+
+
+def test_empty_and_error_paths():
+    """Edge cases: zero sources; call-order and argument errors surface as exceptions, not crashes."""
+    u, v = synthetic.jet_z()
+    w = make_wr(u, v, [1.0, 2.0], np.zeros(0), np.zeros(0), 2.0)
+    w.ray_run(mode="numpy", inte_method="rk45")
+    assert w.rlon.shape == (25, 3, 0, 2) and w.total_accepted == 0
+    with pytest.raises(NotImplementedError):
+        w.ray_run(mode="numpy", inte_method="")
+    with pytest.raises(NotImplementedError):
+        w.ray_run(mode="original", inte_method="rk45")
+    L = lib.load()
+    h = lib.vp()
+    lib.check(L.rwrt_create(0, 144, 73, 1, 1, C.byref(h)))
+    rc = L.rwrt_ray_init(h, 1, None, None, None, 1, None, 0.0, 2, None, None)
+    assert rc != 0 and b"NULL" in L.rwrt_last_error() or b"before" in L.rwrt_last_error()
+    L.rwrt_destroy(h)
+    with pytest.raises(ValueError):
+        lib.check(L.rwrt_create(0, 1, 2, 1, 1, C.byref(h)))
+
+
+def test_poles_and_speed_cutoff_termination():
+    """Rays started next to the pole / in a violent flow terminate with the reference's NaN pattern
+    (compared against the oracle, which follows wr.py:838-850)."""
+    u, v = synthetic.clim(144, 73)
+    u = (u * 6.0).astype(np.float32)     # exaggerated flow: speed cut-off and pole crossings do happen
+    sl, sa = synthetic.random_sources(120, 41, max_abs_lat_deg=88.0)
+    slon, slat = np.radians(sl), np.radians(sa)
+    zwn = np.array([1.0, 2.0, 3.0])
+    ref, acc = oracle_run(u, v, slon, slat, zwn, 10.0)
+    w = make_wr(u, v, zwn, slon, slat, 10.0)
+    w.ray_run(mode="numpy", inte_method="rk45", strict=True)
+    live = ~np.isnan(ref["rmwn"][0])
+    died_ref = np.isnan(ref["rlon"][-1]) & live
+    died_gpu = np.isnan(w.rlon[-1]) & live
+    assert died_ref.sum() > 5
+    assert (died_ref == died_gpu).mean() > 0.97
+    assert set(np.unique(w.status)).issubset({0, 1, 2, 3, 4})
+    assert ((w.status == lib.RAY_ALIVE) == (~np.isnan(w.rlon[-1]) & live)).all()
