@@ -46,11 +46,12 @@ def workload(name, rank=0):
         # weak scaling: every rank integrates a full C2-sized source set, shifted by a fraction of a cell
         slon = (slon + 0.37 * rank / 8.0) % 360.0
         zwn, days = np.arange(1.0, 7.0), 30.0
-    elif name == "c2-small":      # same physics, 1/16 of the sources: quick checks
+    elif name in ("c2-small", "c2-q"):      # same physics, 1/16 or 1/4 of the sources: quick checks / profiling
+        stride = 16 if name == "c2-small" else 4
         nlon, nlat = 360, 181
         u, v = synthetic.clim(nlon, nlat)
         slon, slat = synthetic.all_gridpoint_sources(nlon, nlat, 88.0)
-        slon, slat = slon[rank % 16::16], slat[rank % 16::16]
+        slon, slat = slon[rank % stride::stride], slat[rank % stride::stride]
         zwn, days = np.arange(1.0, 7.0), 30.0
     else:
         raise SystemExit(f"unknown workload {name}")

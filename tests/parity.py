@@ -66,3 +66,35 @@ def compare(got, got_accepted, ref, ref_accepted, nongrazing, label=""):
                 worst_rel_state=worst_rel,
                 grazing_within_tol=int(((dpos < TOL_DEG) & live & ~nongrazing).sum()),
                 steps_total=int(got_accepted.sum()), steps_total_ref=int(ref_accepted.sum()))
+
+
+def oracle_run(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, tstep_h=2.0):
+    """The C oracle on one batch: returns (dict name -> (nt,3,ns,nz), accepted)."""
+    import rwrt_b200  # noqa: F401
+    from rwrt_b200 import synthetic
+    from oracle import oracle
+    lon, lat = synthetic.grid_coords(*u.shape)
+    F = oracle.bs_ready(u, v, lat, True)
+    nt = int(days * 86400.0 / (tstep_h * 3600.0)) + 1
+    out = oracle.ray_init(F, lon, lat, slon_rad, slat_rad, zwn, freq, nt)
+    acc, _ = oracle.ray_run_rk45(F, lon, lat, out, tstep_h * 3600.0, days * 86400.0)
+    return {n: out[k] for k, n in enumerate(NAMES)}, acc
+
+
+def oracle_nongrazing(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, ref=None, acc=None):
+    """Non-grazing mask from the oracle itself: the base run and four runs with the sources moved by
+    +-1 ulp in longitude / latitude must agree to < 1e-7 deg, in NaN pattern and in step counts."""
+    if ref is None:
+        ref, acc = oracle_run(u, v, slon_rad, slat_rad, zwn, days, freq)
+    ng = np.ones(acc.shape, dtype=bool)
+    for a, b in ((np.nextafter(slon_rad, np.inf), slat_rad), (np.nextafter(slon_rad, -np.inf), slat_rad),
+                 (slon_rad, np.nextafter(slat_rad, np.inf)), (slon_rad, np.nextafter(slat_rad, -np.inf))):
+        per, acc_p = oracle_run(u, v, a, b, zwn, days, freq)
+        for n in NAMES:
+            ng &= np.all(np.isnan(ref[n]) == np.isnan(per[n]), axis=0)
+        for n in ("rlon", "rlat"):
+            with np.errstate(invalid="ignore"):
+                d = np.abs(ref[n] - per[n])
+            ng &= np.degrees(np.where(np.isnan(d), 0.0, d).max(axis=0)) < 1e-7
+        ng &= acc == acc_p
+    return ref, acc, ng
