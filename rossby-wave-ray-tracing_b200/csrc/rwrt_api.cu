@@ -81,6 +81,8 @@ struct rwrt_ctx {
         g.dlon = dlon;
         g.lat0 = lat0;
         g.dlat = dlat;
+        g.rdlon = 1.0 / dlon;
+        g.rdlat = 1.0 / dlat;
         return g;
     }
 };

@@ -28,33 +28,49 @@ struct Grid {
     size_t member_stride;  // doubles between members
     int nlon_f, nlat;      // nlon_f = nlon + 1 when xcyclic (wrap column, bs.py:370-372)
     double lon0, dlon, lat0, dlat;  // lon[0], lon[1]-lon[0], lat[0], lat[1]-lat[0] (interpolation.py:78-79)
+    double rdlon, rdlat;            // 1/dlon, 1/dlat (fast build only)
 };
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
-// Python / numpy float remainder by 2*pi (result has the divisor's sign).  fmod is exact.
+// Python / numpy float remainder by 2*pi (result has the divisor's sign).  fmod is exact, and so is this
+// FMA form of it: for the right integer quotient q the remainder a - q*2pi is representable, so one
+// fused multiply-add returns it without rounding; a quotient that is off by one (rounding of a/2pi)
+// shows up as a remainder outside [0, 2pi) and is corrected.  Bit-identical to fmod(), without its loop.
 __device__ __forceinline__ double pymod_2pi(double a)
 {
-    double m = fmod(a, TWOPI);
-    if (m != 0.0) {
-        if (m < 0.0) m += TWOPI;
+    double aa = fabs(a);
+    double r;
+    if (aa < 1.0e9) {
+        double q = floor(aa * (1.0 / TWOPI));
+        r = fma(-q, TWOPI, aa);
+        if (r < 0.0) r = fma(-(q - 1.0), TWOPI, aa);
+        else if (r >= TWOPI) r = fma(-(q + 1.0), TWOPI, aa);
     } else {
-        m = 0.0;
+        r = fmod(aa, TWOPI);  // huge, inf or NaN arguments
     }
-    return m;
+    if (a < 0.0 && r != 0.0) r = TWOPI - r;  // np.remainder: fmod(a, b) + b when the signs differ
+    return r;
 }
 
 // np.maximum: NaN if either operand is NaN
 __device__ __forceinline__ double np_maximum(double a, double b) { return (a != a || b != b) ? qnan() : fmax(a, b); }
 
 // Bilinear sample of the packed fields (interpolation.py:103-135).  f[0..10].
+template <bool FAST>
 __device__ __forceinline__ void sample_packed(const Grid &g, const double *__restrict__ fb, double lon, double lat,
                                               double *f)
 {
-    double l1 = pymod_2pi(lon);  // bs.py:519
-    double l2 = pymod_2pi(l1);   // interpolation.py:80
-    double x = (l2 - g.lon0) / g.dlon;
-    double y = (lat - g.lat0) / g.dlat;
+    double l1 = pymod_2pi(lon);            // bs.py:519
+    double l2 = (l1 >= TWOPI) ? 0.0 : l1;  // interpolation.py:80: a second % 2pi only moves an exact 2pi to 0
+    double x, y;
+    if (FAST) {
+        x = (l2 - g.lon0) * g.rdlon;
+        y = (lat - g.lat0) * g.rdlat;
+    } else {
+        x = (l2 - g.lon0) / g.dlon;
+        y = (lat - g.lat0) / g.dlat;
+    }
     const int W = g.nlon_f, H = g.nlat;
     int x0u = __double2int_rd(x), y0u = __double2int_rd(y);  // floor -> int32 (NaN -> 0 after the clamp either way)
     int x0 = min(max(x0u, 0), W - 1), y0 = min(max(y0u, 0), H - 1);
@@ -79,37 +95,59 @@ struct Merc {
     double cosl, sinl;
 };
 
+template <bool FAST>
 __device__ __forceinline__ Merc sample_mercator(const Grid &g, const double *__restrict__ fb, double lon, double lat)
 {
     Merc m;
     if (!(fabs(lat) <= HALFPI)) {  // bs.py:787: rows outside +-pi/2 (or NaN) stay NaN
         double n = qnan();
         m.u = m.v = m.ux = m.uy = m.vx = m.vy = m.qx = m.qy = m.qxx = m.qxy = m.qyx = m.qyy = n;
-        m.cosl = cos(lat);
-        m.sinl = sin(lat);
+        m.cosl = n;
+        m.sinl = n;
         return m;
     }
     double f[12];
-    sample_packed(g, fb, lon, lat, f);
+    sample_packed<FAST>(g, fb, lon, lat, f);
     double fu = f[0], fv = f[1], fux = f[2], fuy = f[3], fvx = f[4], fvy = f[5], fqx = f[6], fqy = f[7], fqxx = f[8],
            fqxy = f[9], fqyy = f[10];
-    double cp = cos(lat), sp = sin(lat), tl = tan(lat);
+    double cp, sp, tl;
+    if (FAST) {
+        sincos(lat, &sp, &cp);
+        tl = sp / cp;
+    } else {
+        cp = cos(lat);
+        sp = sin(lat);
+        tl = tan(lat);
+    }
     m.cosl = cp;
     m.sinl = sp;
-    double mask = (fabs(cp) <= 0.0175) ? 0.0 : 1.0;
-    cp = cp * mask + (1 - mask) * 1e-6;
-    m.qxx = fqxx * mask;
-    m.qyx = fqxy * cp * mask;
-    m.qxy = m.qyx * mask;
-    m.qyy = (fqyy * cp - fqy * sp) * cp * mask;
-    m.qx = fqx * mask;
-    m.qy = fqy * cp * mask;
-    m.ux = fux / cp * mask;
-    m.vx = fvx / cp * mask;
-    m.uy = (fuy + tl * fu) * mask;
-    m.vy = (fvy + tl * fv) * mask;
-    m.u = fu / cp * mask;
-    m.v = fv / cp * mask;
+    if (fabs(cp) <= 0.0175) {  // bs.py:858-883 with mask = 0: every Mercator quantity is multiplied by zero
+        // (cos -> 1e-6 there, so nothing overflows and the products are exact zeros unless a field is NaN)
+        double z = (fu + fv + fux + fuy + fvx + fvy + fqx + fqy + fqxx + fqxy + fqyy) * 0.0;
+        m.u = m.v = m.ux = m.uy = m.vx = m.vy = m.qx = m.qy = m.qxx = m.qxy = m.qyx = m.qyy = z;
+        return m;
+    }
+    // mask = 1: cos_phi * 1 + 0 * 1e-6 = cos_phi, and the trailing "* mask" factors are exact
+    m.qxx = fqxx;
+    m.qyx = fqxy * cp;
+    m.qxy = m.qyx;
+    m.qyy = (fqyy * cp - fqy * sp) * cp;
+    m.qx = fqx;
+    m.qy = fqy * cp;
+    m.uy = fuy + tl * fu;
+    m.vy = fvy + tl * fv;
+    if (FAST) {
+        double rc = 1.0 / cp;
+        m.ux = fux * rc;
+        m.vx = fvx * rc;
+        m.u = fu * rc;
+        m.v = fv * rc;
+    } else {
+        m.ux = fux / cp;
+        m.vx = fvx / cp;
+        m.u = fu / cp;
+        m.v = fv / cp;
+    }
     return m;
 }
 
@@ -142,6 +180,10 @@ __device__ __forceinline__ void ugvg_numpy(double fu, double fv, double fqx, dou
 }
 
 // One right-hand side: wr.py:784-789 -> 492-556 -> 44-82.  y = (lon, lat, k, l, A).
+// FAST: same formulas with the shared denominators inverted once (1 reciprocal instead of 7 divisions
+// in the wavenumber algebra, multiplication by 1/a instead of 5 divisions) -- differences are at the
+// level of one rounding per operation, like FMA contraction.
+template <bool FAST>
 __device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict__ fb, const double *y, double *dy)
 {
     double lon = y[0], lat = y[1], kx = y[2], ky = y[3], amp = y[4];
@@ -151,7 +193,33 @@ __device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict_
         dy[0] = dy[1] = dy[2] = dy[3] = dy[4] = n;  // wr.py:552-553
         return;
     }
-    Merc m = sample_mercator(g, fb, lon, lat);
+    Merc m = sample_mercator<FAST>(g, fb, lon, lat);
+    if (FAST) {
+        double k2 = kx * kx, l2 = ky * ky;
+        double K2 = k2 + l2;                 // = kk = kx^2 (1 + kap^2)
+        double r = 1.0 / (kx * K2 * K2);     // one reciprocal for 1/kx, 1/kk, 1/kap1, 1/(kk kap1)
+        double rk = r * K2 * K2;             // 1/kx
+        double kap = ky * rk;
+        double kap2 = kap * kap;
+        double rkk = r * kx * K2;            // 1/kk
+        double rkap1 = k2 * rkk;             // 1/kap1 = kx^2 / kk
+        double rden = rkk * rkap1;           // 1/(kk kap1)
+        double ug = m.u + (((1. - kap2) * m.qy) - (2. * kap * m.qx)) * rden;
+        double vg = m.v + ((2. * kap * m.qy) + ((1. - kap2) * m.qx)) * rden;
+        double dzwn = -kx * ((m.ux + kap * m.vx) + (kap * m.qxx - m.qyx) * rkk);
+        double dmwn = -kx * ((m.uy + kap * m.vy) + (kap * m.qxy - m.qyy) * rkk);
+        double damp1 = 2.0 * (m.ux + m.vy + kap * (m.vx + m.uy)) * rkap1;
+        double damp2 = 2.0 * (kap * (m.qxx - m.qyy) + (kap2 - 1.0) * m.qxy) * rden;
+        double damp3 = -2.0 * m.sinl * m.v;
+        double damp = damp1 + damp2 + damp3;
+        const double ra = 1.0 / REARTH;
+        dy[0] = ug * ra;
+        dy[1] = (vg * m.cosl) * ra;
+        dy[2] = dzwn * ra;
+        dy[3] = dmwn * ra;
+        dy[4] = (damp * amp) * ra;
+        return;
+    }
     double ug, vg;
     ugvg_extent(m.u, m.v, m.qx, m.qy, kx, ky, ug, vg);
     double kap = ky / kx;

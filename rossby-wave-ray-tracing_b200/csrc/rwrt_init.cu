@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(128) ray_init_kernel(Grid g, int nsource, cons
     int s = (int)(idx / nzwn), iz = (int)(idx % nzwn);
     const double *fb = g.fpk + (src_member ? (size_t)src_member[s] * g.member_stride : 0);
     double lon = src_lon[s], lat = src_lat[s], k = zwn[iz];
-    Merc m = sample_mercator(g, fb, lon, lat);  // wr.py:360-365
+    Merc m = sample_mercator<false>(g, fb, lon, lat);  // wr.py:360-365
     double l[3];
     cal_ky_point(m.u, m.v, m.qx, m.qy, freq, k, l);
     const size_t N = (size_t)3 * nsource * nzwn, pl = (size_t)nt * N;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(128) sample_kernel(Grid g, long long n, const 
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double *fb = g.fpk + (member ? (size_t)member[i] * g.member_stride : 0);
-    Merc m = sample_mercator(g, fb, lon[i], lat[i]);
+    Merc m = sample_mercator<false>(g, fb, lon[i], lat[i]);
     out[0 * n + i] = m.u;
     out[1 * n + i] = m.v;
     out[2 * n + i] = m.ux;

@@ -83,7 +83,7 @@ __device__ double initial_step(const Grid &g, const double *fb, const double *y0
     if (d1 < 1e-5) h0 = 1e-6;
 #pragma unroll
     for (int c = 0; c < 5; ++c) y1[c] = y0[c] + h0 * 1.0 * f0[c];
-    ray_rhs(g, fb, y1, f1);
+    ray_rhs<RWRT_FAST>(g, fb, y1, f1);
     double d2 = rms5((f1[0] - f0[0]) / scale[0], (f1[1] - f0[1]) / scale[1], (f1[2] - f0[2]) / scale[2],
                      (f1[3] - f0[3]) / scale[3], (f1[4] - f0[4]) / scale[4]) / h0;
     bool m1 = !(d1 > 1e-15), m2 = !(d2 > 1e-15);
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) rk45_prepare(RunParams p)
 #pragma unroll
     for (int c = 0; c < 5; ++c) y[c] = p.out[c * pl + slot];
     const double *fb = member_base(p, slot);
-    ray_rhs(p.g, fb, y, f);
+    ray_rhs<RWRT_FAST>(p.g, fb, y, f);
     double h = initial_step(p.g, fb, y, f, p.rtol, p.atol);
     double *st = p.state + (size_t)i * 12;
 #pragma unroll
@@ -144,15 +144,21 @@ __global__ void __launch_bounds__(256) fill_static_slots(RunParams p)
     }
 }
 
+// Per-lane ray state kept in registers; the seven stage vectors K1..K7 live in shared memory
+// (ks[stage][component][thread], conflict-free), which keeps the kernel at <= 128 registers and
+// 16 resident warps per SM instead of 8.
 struct Lane {
-    double y[5], f[5];
+    double y[5];
     double t, h_abs, plon, plat;
     long long slot;
-    long long acc, att;
+    int acc, att;
     int it;         // next output row to produce
     bool rejected;  // a rejection happened since the last accepted step (rkf45.py:462-469)
     bool fresh;     // next attempt is the first of a pass: apply the min-step clamp (rkf45.py:383-387)
 };
+
+constexpr int RK_THREADS = 128;
+constexpr int RK_SMEM_BYTES = 7 * 5 * RK_THREADS * (int)sizeof(double);
 
 __device__ __forceinline__ void write_row(const RunParams &p, long long slot, int it, double lon, double lat, double k,
                                           double l, double a, double ug, double vg)
@@ -168,11 +174,28 @@ __device__ __forceinline__ void write_row(const RunParams &p, long long slot, in
     p.out[6 * pl + o] = vg;
 }
 
-// The integrator.  Persistent grid; every lane owns one ray at a time.
-__global__ void __launch_bounds__(128) rk45_integrate(RunParams p)
+// rkf45.py:453-455 / 474-475: 0.9 * err^-0.2 clipped to [0.2, 10].  The clip makes pow() unnecessary
+// outside (5e-6, 2000): there the clipped value does not depend on pow's rounding.
+__device__ __forceinline__ double step_factor(double err, bool accept)
 {
+    if (accept) {
+        if (err < 5.0e-6) return 10.0;  // 0.9 * err^-0.2 > 10.3 (also err == 0, rkf45.py:455)
+        double f = 0.9 * pow(err, -0.2);
+        return f < 10.0 ? f : 10.0;
+    }
+    if (err > 2000.0) return 0.2;       // 0.9 * err^-0.2 < 0.197
+    double f = 0.9 * pow(err, -0.2);
+    return f > 0.2 ? f : 0.2;
+}
+
+// The integrator.  Persistent grid; every lane owns one ray at a time.
+__global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
+{
+    extern __shared__ double ks[];  // [7][5][RK_THREADS]
     const unsigned FULL = 0xffffffffu;
-    const int lane_id = threadIdx.x & 31;
+    const int tid = threadIdx.x;
+    const int lane_id = tid & 31;
+#define KS(s, c) ks[((s) * 5 + (c)) * RK_THREADS + tid]
     Lane L;
     L.slot = -1;
     const double *fb = p.g.fpk;
@@ -197,7 +220,10 @@ __global__ void __launch_bounds__(128) rk45_integrate(RunParams p)
                     const double *st = p.state + (size_t)mine * 12;
                     L.slot = p.live[mine];
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) { L.y[c] = st[c]; L.f[c] = st[5 + c]; }
+                    for (int c = 0; c < 5; ++c) {
+                        L.y[c] = st[c];
+                        KS(0, c) = st[5 + c];
+                    }
                     L.h_abs = st[10];
                     L.t = 0.0;
                     L.plon = L.y[0];
@@ -223,59 +249,71 @@ __global__ void __launch_bounds__(128) rk45_integrate(RunParams p)
         }
         double t_new = L.t + L.h_abs;  // rkf45.py:426-435
         if (t_new - tb > 0) t_new = tb;
-        double h = t_new - L.t;
-        double h_abs = fabs(h);
+        const double h = t_new - L.t;
         ++L.att;
-        double k2[5], k3[5], k4[5], k5[5], k6[5], k7[5], ys[5], yn[5];
-        const double *k1 = L.f;
+        double ys[5], kn[5];
         // rkf45.py:306-311: dy = (sum_j K_j a_sj) * h, accumulated in j order
 #pragma unroll
-        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * A21) * h;
-        ray_rhs(p.g, fb, ys, k2);
+        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (KS(0, c) * A21) * h;
+        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * A31 + k2[c] * A32) * h;
-        ray_rhs(p.g, fb, ys, k3);
+        for (int c = 0; c < 5; ++c) {
+            KS(1, c) = kn[c];
+            ys[c] = L.y[c] + (KS(0, c) * A31 + kn[c] * A32) * h;
+        }
+        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * A41 + k2[c] * A42 + k3[c] * A43) * h;
-        ray_rhs(p.g, fb, ys, k4);
+        for (int c = 0; c < 5; ++c) {
+            KS(2, c) = kn[c];
+            ys[c] = L.y[c] + (KS(0, c) * A41 + KS(1, c) * A42 + kn[c] * A43) * h;
+        }
+        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * A51 + k2[c] * A52 + k3[c] * A53 + k4[c] * A54) * h;
-        ray_rhs(p.g, fb, ys, k5);
+        for (int c = 0; c < 5; ++c) {
+            KS(3, c) = kn[c];
+            ys[c] = L.y[c] + (KS(0, c) * A51 + KS(1, c) * A52 + KS(2, c) * A53 + kn[c] * A54) * h;
+        }
+        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
 #pragma unroll
-        for (int c = 0; c < 5; ++c)
-            ys[c] = L.y[c] + (k1[c] * A61 + k2[c] * A62 + k3[c] * A63 + k4[c] * A64 + k5[c] * A65) * h;
-        ray_rhs(p.g, fb, ys, k6);
+        for (int c = 0; c < 5; ++c) {
+            KS(4, c) = kn[c];
+            ys[c] = L.y[c] + (KS(0, c) * A61 + KS(1, c) * A62 + KS(2, c) * A63 + KS(3, c) * A64 + kn[c] * A65) * h;
+        }
+        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
 #pragma unroll
-        for (int c = 0; c < 5; ++c)  // rkf45.py:316 (the zero B2 term is part of the einsum)
-            yn[c] = L.y[c] + h * (k1[c] * B1 + k2[c] * B2 + k3[c] * B3 + k4[c] * B4 + k5[c] * B5 + k6[c] * B6);
-        ray_rhs(p.g, fb, yn, k7);  // rkf45.py:317-319
+        for (int c = 0; c < 5; ++c) {  // rkf45.py:316 (the zero B2 term is part of the einsum)
+            KS(5, c) = kn[c];
+            ys[c] = L.y[c] + h * (KS(0, c) * B1 + KS(1, c) * B2 + KS(2, c) * B3 + KS(3, c) * B4 + KS(4, c) * B5 + kn[c] * B6);
+        }
+        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);  // rkf45.py:317-319: ys now holds y_new, kn = f(y_new)
         double r[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {  // rkf45.py:442-446
-            double scale = p.atol + np_maximum(fabs(L.y[c]), fabs(yn[c])) * p.rtol;
-            double e = k1[c] * E1 + k2[c] * E2 + k3[c] * E3 + k4[c] * E4 + k5[c] * E5 + k6[c] * E6 + k7[c] * E7;
+            double scale = p.atol + np_maximum(fabs(L.y[c]), fabs(ys[c])) * p.rtol;
+            double e = KS(0, c) * E1 + KS(1, c) * E2 + KS(2, c) * E3 + KS(3, c) * E4 + KS(4, c) * E5 + KS(5, c) * E6 +
+                       kn[c] * E7;
             r[c] = (h * e) / scale;
         }
         double err = rms5(r[0], r[1], r[2], r[3], r[4]);
         if (err != err) err = 0;
-        bool accept = err < 1;
-        double factor = 0.9 * pow(err, -0.2);
-        if (accept) {  // rkf45.py:449-471
-            if (!(factor < 10)) factor = 10;
-            if (err == 0) factor = 10;
-            if (L.rejected && factor > 1.0) factor = 1.0;
-        } else {  // rkf45.py:474-479
-            if (!(factor > 0.2)) factor = 0.2;
+        const bool accept = err < 1;
+        double factor = step_factor(err, accept);
+        if (accept) {
+            if (L.rejected && factor > 1.0) factor = 1.0;  // rkf45.py:462-469
+        } else {
             L.rejected = true;
         }
-        L.h_abs = h_abs * factor;
+        L.h_abs = fabs(h) * factor;
         if (!accept) continue;
 
         // ---- accepted step ----
         ++L.acc;
         L.t = (t_new != t_new) ? tb : t_new;  // rkf45.py:503
 #pragma unroll
-        for (int c = 0; c < 5; ++c) { L.y[c] = yn[c]; L.f[c] = k7[c]; }
+        for (int c = 0; c < 5; ++c) {
+            L.y[c] = ys[c];
+            KS(0, c) = kn[c];  // FSAL: f(y_new) is the next pass's self.f (rkf45.py:378 recomputes the same value)
+        }
         L.fresh = true;
         double ysum = L.y[0] + L.y[1] + L.y[2] + L.y[3] + L.y[4];  // np.mean(y) is NaN (rkf45.py:400-402)
         bool dead = (ysum != ysum);
@@ -299,7 +337,7 @@ __global__ void __launch_bounds__(128) rk45_integrate(RunParams p)
             double n = qnan();
             for (int it = L.it; it < p.nt; ++it) write_row(p, L.slot, it, n, n, n, n, n, n, n);
         } else {
-            Merc m = sample_mercator(p.g, fb, L.y[0], L.y[1]);  // wr.py:856-865
+            Merc m = sample_mercator<RWRT_FAST>(p.g, fb, L.y[0], L.y[1]);  // wr.py:856-865
             double ug, vg;
             ugvg_extent(m.u, m.v, m.qx, m.qy, L.y[2], L.y[3], ug, vg);
             write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
@@ -315,7 +353,8 @@ __global__ void __launch_bounds__(128) rk45_integrate(RunParams p)
             L.slot = -1;
         }
     }
-    // block-level reduction of the accepted-step total (the metric), one atomic per warp
+#undef KS
+    // warp-level reduction of the accepted-step total (the metric), one atomic per warp
     for (int o = 16; o > 0; o >>= 1) my_total += __shfl_down_sync(FULL, my_total, o);
     if (lane_id == 0 && my_total) atomicAdd(p.total_accepted, (unsigned long long)my_total);
 }

@@ -1,5 +1,6 @@
 // Strict build of the RK45 kernels: compiled with -fmad=false (see build.py).
 #define RWRT_VARIANT strict
+#define RWRT_FAST false
 #include "rwrt_rk45.cuh"
 #include "rwrt_internal.h"
 
@@ -9,13 +10,14 @@ void launch_rk45_strict(const RunParams &p, int prepare_blocks, int fill_blocks,
     if (p.N > 0 && p.nt > 1) strict::fill_static_slots<<<dim3(fill_blocks, p.nt - 1), 256, 0, s>>>(p);
     if (p.nlive > 0) {
         strict::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
-        strict::rk45_integrate<<<integrate_blocks, 128, 0, s>>>(p);
+        strict::rk45_integrate<<<integrate_blocks, strict::RK_THREADS, strict::RK_SMEM_BYTES, s>>>(p);
     }
 }
 int occupancy_rk45_strict()
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, strict::rk45_integrate, 128, 0);
+    cudaFuncSetAttribute(strict::rk45_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::RK_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, strict::rk45_integrate, strict::RK_THREADS, strict::RK_SMEM_BYTES);
     return nb;
 }
 __global__ void rhs_kernel_strict(Grid g, long long n, const double *y, const int32_t *member, double *dy)
@@ -25,7 +27,7 @@ __global__ void rhs_kernel_strict(Grid g, long long n, const double *y, const in
     double yy[5], d[5];
     for (int c = 0; c < 5; ++c) yy[c] = y[c * n + i];
     const double *fb = g.fpk + (member ? (size_t)member[i] * g.member_stride : 0);
-    ray_rhs(g, fb, yy, d);
+    ray_rhs<RWRT_FAST>(g, fb, yy, d);
     for (int c = 0; c < 5; ++c) dy[c * n + i] = d[c];
 }
 void launch_rhs_strict(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s)
