@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -423,6 +424,10 @@ int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int
     bool strict = (flags & RWRT_MODE_STRICT) != 0;
     int per_sm = strict ? occupancy_rk45_strict() : occupancy_rk45_fast();
     if (per_sm < 1) per_sm = 1;
+    if (const char *e = getenv("RWRT_BLOCKS_PER_SM")) {  // tuning knob (profiles/): cap resident blocks per SM
+        int v = atoi(e);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     long long want = ((long long)nlive + 127) / 128;
     int integrate_blocks = (int)(want < (long long)per_sm * h->sm_count ? want : (long long)per_sm * h->sm_count);
     if (integrate_blocks < 1) integrate_blocks = 1;

@@ -183,14 +183,20 @@ __device__ __forceinline__ void ugvg_numpy(double fu, double fv, double fqx, dou
 // FAST: same formulas with the shared denominators inverted once (1 reciprocal instead of 7 divisions
 // in the wavenumber algebra, multiplication by 1/a instead of 5 divisions) -- differences are at the
 // level of one rounding per operation, like FMA contraction.
+// ugo / vgo: the group velocity at y (m/s), which is also what the reference stores at output times
+// (wr.py:856-865 re-samples at the same point with the same formula).  *masked is set when the
+// |lat| / |l| mask fired (then ugo / vgo are not computed here).
 template <bool FAST>
-__device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict__ fb, const double *y, double *dy)
+__device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict__ fb, const double *y, double *dy,
+                                        double &ugo, double &vgo, bool &masked)
 {
     double lon = y[0], lat = y[1], kx = y[2], ky = y[3], amp = y[4];
     bool err = (fabs(lat) >= HALFPI) || (fabs(ky) >= 100.0);  // wr.py:508-510
+    masked = err;
     if (err) {
         double n = qnan();
         dy[0] = dy[1] = dy[2] = dy[3] = dy[4] = n;  // wr.py:552-553
+        ugo = vgo = n;
         return;
     }
     Merc m = sample_mercator<FAST>(g, fb, lon, lat);
@@ -218,6 +224,8 @@ __device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict_
         dy[2] = dzwn * ra;
         dy[3] = dmwn * ra;
         dy[4] = (damp * amp) * ra;
+        ugo = ug;
+        vgo = vg;
         return;
     }
     double ug, vg;
@@ -237,6 +245,16 @@ __device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict_
     dy[2] = dzwn / REARTH;
     dy[3] = dmwn / REARTH;
     dy[4] = (damp * amp) / REARTH;
+    ugo = ug;
+    vgo = vg;
+}
+
+template <bool FAST>
+__device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict__ fb, const double *y, double *dy)
+{
+    double ug, vg;
+    bool masked;
+    ray_rhs<FAST>(g, fb, y, dy, ug, vg, masked);
 }
 
 // wr.py:97-112

@@ -188,7 +188,31 @@ __device__ __forceinline__ double step_factor(double err, bool accept)
     return f > 0.2 ? f : 0.2;
 }
 
-// The integrator.  Persistent grid; every lane owns one ray at a time.
+// Output-time group velocity when the RHS mask fired at an output point (|l| >= 100 there): the
+// reference still samples and evaluates wn.py:266-294 without the mask (wr.py:856-865).  Rare; kept out
+// of line so the hot loop holds a single instance of the sampler.
+__device__ __noinline__ double2 output_ugvg_slow(Grid g, const double *fb, double lon, double lat, double k, double l)
+{
+    Merc m = sample_mercator<RWRT_FAST>(g, fb, lon, lat);
+    double2 r;
+    ugvg_extent(m.u, m.v, m.qx, m.qy, k, l, r.x, r.y);
+    return r;
+}
+
+// Stage coefficients: rows 1..5 = A (rkf45.py:605-612), row 6 = B (rkf45.py:613) -- the sums
+// sum_j K_j c_sj are accumulated in j order exactly like the reference's einsum.
+__constant__ double cC[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+
+// The integrator.  Persistent grid; every lane owns one ray at a time.  The six stages run through ONE
+// instance of the right-hand side (a loop, not six inlined copies): the kernel stays inside the
+// instruction cache (v2, fully unrolled, spent 27 % of its warp time on instruction-fetch stalls).
 __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
 {
     extern __shared__ double ks[];  // [7][5][RK_THREADS]
@@ -251,41 +275,22 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
         if (t_new - tb > 0) t_new = tb;
         const double h = t_new - L.t;
         ++L.att;
-        double ys[5], kn[5];
-        // rkf45.py:306-311: dy = (sum_j K_j a_sj) * h, accumulated in j order
+        double ys[5], kn[5], ug = 0, vg = 0;
+        bool masked = false;
+#pragma unroll 1
+        for (int s = 1; s <= 6; ++s) {
+            // rkf45.py:306-311 / 316: y + (sum_{j<s} K_j c_sj) * h, the sum accumulated in j order
 #pragma unroll
-        for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (KS(0, c) * A21) * h;
-        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
+            for (int c = 0; c < 5; ++c) {
+                double a = KS(0, c) * cC[s][0];
+                for (int j = 1; j < s; ++j) a = a + KS(j, c) * cC[s][j];
+                ys[c] = L.y[c] + a * h;
+            }
+            ray_rhs<RWRT_FAST>(p.g, fb, ys, kn, ug, vg, masked);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            KS(1, c) = kn[c];
-            ys[c] = L.y[c] + (KS(0, c) * A31 + kn[c] * A32) * h;
+            for (int c = 0; c < 5; ++c) KS(s, c) = kn[c];
         }
-        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            KS(2, c) = kn[c];
-            ys[c] = L.y[c] + (KS(0, c) * A41 + KS(1, c) * A42 + kn[c] * A43) * h;
-        }
-        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            KS(3, c) = kn[c];
-            ys[c] = L.y[c] + (KS(0, c) * A51 + KS(1, c) * A52 + KS(2, c) * A53 + kn[c] * A54) * h;
-        }
-        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            KS(4, c) = kn[c];
-            ys[c] = L.y[c] + (KS(0, c) * A61 + KS(1, c) * A62 + KS(2, c) * A63 + KS(3, c) * A64 + kn[c] * A65) * h;
-        }
-        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {  // rkf45.py:316 (the zero B2 term is part of the einsum)
-            KS(5, c) = kn[c];
-            ys[c] = L.y[c] + h * (KS(0, c) * B1 + KS(1, c) * B2 + KS(2, c) * B3 + KS(3, c) * B4 + KS(4, c) * B5 + kn[c] * B6);
-        }
-        ray_rhs<RWRT_FAST>(p.g, fb, ys, kn);  // rkf45.py:317-319: ys now holds y_new, kn = f(y_new)
+        // now ys = y_new and KS(6, .) = kn = f(y_new) (rkf45.py:317-319)
         double r[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {  // rkf45.py:442-446
@@ -337,9 +342,12 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
             double n = qnan();
             for (int it = L.it; it < p.nt; ++it) write_row(p, L.slot, it, n, n, n, n, n, n, n);
         } else {
-            Merc m = sample_mercator<RWRT_FAST>(p.g, fb, L.y[0], L.y[1]);  // wr.py:856-865
-            double ug, vg;
-            ugvg_extent(m.u, m.v, m.qx, m.qy, L.y[2], L.y[3], ug, vg);
+            // wr.py:856-865: ug, vg at the output point = what the last stage evaluated at y_new
+            if (masked) {
+                double2 gv = output_ugvg_slow(p.g, fb, L.y[0], L.y[1], L.y[2], L.y[3]);
+                ug = gv.x;
+                vg = gv.y;
+            }
             write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
             L.plon = L.y[0];
             L.plat = L.y[1];
