@@ -22,6 +22,7 @@ constexpr double REARTH = 6.3712e6;                                           //
 constexpr double OMEGA = 7.2921e-5;                                           // constants.py:17
 constexpr double DELT = 1.0e-8;                                               // constants.py:28
 constexpr int NPK = 12;  // doubles per packed grid point
+constexpr int NCELL = 48;  // doubles per cell record: 11 fields x 4 corners (a,b,c,d) + 4 pad = 384 B = 3 lines
 
 struct Grid {
     const double *fpk;     // (nmember, nlon_f, nlat, NPK)
@@ -29,6 +30,8 @@ struct Grid {
     int nlon_f, nlat;      // nlon_f = nlon + 1 when xcyclic (wrap column, bs.py:370-372)
     double lon0, dlon, lat0, dlat;  // lon[0], lon[1]-lon[0], lat[0], lat[1]-lat[0] (interpolation.py:78-79)
     double rdlon, rdlat;            // 1/dlon, 1/dlat (fast build only)
+    const double *fcell;            // optional cell-major table (nmember, nlon_f, nlat, NCELL) or nullptr
+    size_t cell_member_stride;      // doubles between members in fcell
 };
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -57,9 +60,10 @@ __device__ __forceinline__ double pymod_2pi(double a)
 __device__ __forceinline__ double np_maximum(double a, double b) { return (a != a || b != b) ? qnan() : fmax(a, b); }
 
 // Bilinear sample of the packed fields (interpolation.py:103-135).  f[0..10].
+// interpolation.py:77-85 + 112-130: fractional indices, floor -> int32, clamp, weights from the CLAMPED indices
 template <bool FAST>
-__device__ __forceinline__ void sample_packed(const Grid &g, const double *__restrict__ fb, double lon, double lat,
-                                              double *f)
+__device__ __forceinline__ void locate(const Grid &g, double lon, double lat, int &x0, int &y0, int &x1, int &y1,
+                                       double &sx, double &sy)
 {
     double l1 = pymod_2pi(lon);            // bs.py:519
     double l2 = (l1 >= TWOPI) ? 0.0 : l1;  // interpolation.py:80: a second % 2pi only moves an exact 2pi to 0
@@ -73,9 +77,23 @@ __device__ __forceinline__ void sample_packed(const Grid &g, const double *__res
     }
     const int W = g.nlon_f, H = g.nlat;
     int x0u = __double2int_rd(x), y0u = __double2int_rd(y);  // floor -> int32 (NaN -> 0 after the clamp either way)
-    int x0 = min(max(x0u, 0), W - 1), y0 = min(max(y0u, 0), H - 1);
-    int x1 = min(max(x0u + 1, 0), W - 1), y1 = min(max(y0u + 1, 0), H - 1);
-    double sx = x - (double)x0, sy = y - (double)y0;  // weights from the CLAMPED indices
+    x0 = min(max(x0u, 0), W - 1);
+    y0 = min(max(y0u, 0), H - 1);
+    x1 = min(max(x0u + 1, 0), W - 1);
+    y1 = min(max(y0u + 1, 0), H - 1);
+    sx = x - (double)x0;
+    sy = y - (double)y0;
+}
+
+// Bilinear sample of the packed fields (interpolation.py:103-135).  f[0..10].
+template <bool FAST>
+__device__ __forceinline__ void sample_packed(const Grid &g, const double *__restrict__ fb, double lon, double lat,
+                                              double *f)
+{
+    int x0, y0, x1, y1;
+    double sx, sy;
+    locate<FAST>(g, lon, lat, x0, y0, x1, y1, sx, sy);
+    const int H = g.nlat;
     double wa = (1 - sx) * sy, wb = sx * sy, wc = (1 - sx) * (1 - sy), wd = sx * (1 - sy);
     const double2 *pa = reinterpret_cast<const double2 *>(fb + ((size_t)x0 * H + y1) * NPK);
     const double2 *pb = reinterpret_cast<const double2 *>(fb + ((size_t)x1 * H + y1) * NPK);
@@ -95,30 +113,33 @@ struct Merc {
     double cosl, sinl;
 };
 
+// cos / sin / tan of the latitude as bs.py:856-857, 876-877 evaluate them (FAST: one sincos and a division)
+struct Trig {
+    double cp, sp, tl;
+};
 template <bool FAST>
-__device__ __forceinline__ Merc sample_mercator(const Grid &g, const double *__restrict__ fb, double lon, double lat)
+__device__ __forceinline__ Trig trig_of_lat(double lat)
+{
+    Trig t;
+    if (FAST) {
+        sincos(lat, &t.sp, &t.cp);
+        t.tl = t.sp / t.cp;
+    } else {
+        t.cp = cos(lat);
+        t.sp = sin(lat);
+        t.tl = tan(lat);
+    }
+    return t;
+}
+
+// bs.py:856-883 applied to the 11 interpolated fields f at a latitude with |lat| <= pi/2
+template <bool FAST>
+__device__ __forceinline__ Merc mercator_from_fields(const double *f, const Trig &tg)
 {
     Merc m;
-    if (!(fabs(lat) <= HALFPI)) {  // bs.py:787: rows outside +-pi/2 (or NaN) stay NaN
-        double n = qnan();
-        m.u = m.v = m.ux = m.uy = m.vx = m.vy = m.qx = m.qy = m.qxx = m.qxy = m.qyx = m.qyy = n;
-        m.cosl = n;
-        m.sinl = n;
-        return m;
-    }
-    double f[12];
-    sample_packed<FAST>(g, fb, lon, lat, f);
     double fu = f[0], fv = f[1], fux = f[2], fuy = f[3], fvx = f[4], fvy = f[5], fqx = f[6], fqy = f[7], fqxx = f[8],
            fqxy = f[9], fqyy = f[10];
-    double cp, sp, tl;
-    if (FAST) {
-        sincos(lat, &sp, &cp);
-        tl = sp / cp;
-    } else {
-        cp = cos(lat);
-        sp = sin(lat);
-        tl = tan(lat);
-    }
+    const double cp = tg.cp, sp = tg.sp, tl = tg.tl;
     m.cosl = cp;
     m.sinl = sp;
     if (fabs(cp) <= 0.0175) {  // bs.py:858-883 with mask = 0: every Mercator quantity is multiplied by zero
@@ -149,6 +170,22 @@ __device__ __forceinline__ Merc sample_mercator(const Grid &g, const double *__r
         m.v = fv / cp;
     }
     return m;
+}
+
+template <bool FAST>
+__device__ __forceinline__ Merc sample_mercator(const Grid &g, const double *__restrict__ fb, double lon, double lat)
+{
+    if (!(fabs(lat) <= HALFPI)) {  // bs.py:787: rows outside +-pi/2 (or NaN) stay NaN
+        Merc m;
+        double n = qnan();
+        m.u = m.v = m.ux = m.uy = m.vx = m.vy = m.qx = m.qy = m.qxx = m.qxy = m.qyx = m.qyy = n;
+        m.cosl = n;
+        m.sinl = n;
+        return m;
+    }
+    double f[12];
+    sample_packed<FAST>(g, fb, lon, lat, f);
+    return mercator_from_fields<FAST>(f, trig_of_lat<FAST>(lat));
 }
 
 // wn.py:266-294
@@ -183,23 +220,10 @@ __device__ __forceinline__ void ugvg_numpy(double fu, double fv, double fqx, dou
 // FAST: same formulas with the shared denominators inverted once (1 reciprocal instead of 7 divisions
 // in the wavenumber algebra, multiplication by 1/a instead of 5 divisions) -- differences are at the
 // level of one rounding per operation, like FMA contraction.
-// ugo / vgo: the group velocity at y (m/s), which is also what the reference stores at output times
-// (wr.py:856-865 re-samples at the same point with the same formula).  *masked is set when the
-// |lat| / |l| mask fired (then ugo / vgo are not computed here).
 template <bool FAST>
-__device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict__ fb, const double *y, double *dy,
-                                        double &ugo, double &vgo, bool &masked)
+__device__ __forceinline__ void rhs_from_merc(const Merc &m, const double *y, double *dy, double &ugo, double &vgo)
 {
-    double lon = y[0], lat = y[1], kx = y[2], ky = y[3], amp = y[4];
-    bool err = (fabs(lat) >= HALFPI) || (fabs(ky) >= 100.0);  // wr.py:508-510
-    masked = err;
-    if (err) {
-        double n = qnan();
-        dy[0] = dy[1] = dy[2] = dy[3] = dy[4] = n;  // wr.py:552-553
-        ugo = vgo = n;
-        return;
-    }
-    Merc m = sample_mercator<FAST>(g, fb, lon, lat);
+    double kx = y[2], ky = y[3], amp = y[4];
     if (FAST) {
         double k2 = kx * kx, l2 = ky * ky;
         double K2 = k2 + l2;                 // = kk = kx^2 (1 + kap^2)
@@ -247,6 +271,26 @@ __device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict_
     dy[4] = (damp * amp) / REARTH;
     ugo = ug;
     vgo = vg;
+}
+
+// ugo / vgo: the group velocity at y (m/s), which is also what the reference stores at output times
+// (wr.py:856-865 re-samples at the same point with the same formula).  masked is set when the
+// |lat| / |l| mask fired (then ugo / vgo are not computed here).
+template <bool FAST>
+__device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict__ fb, const double *y, double *dy,
+                                        double &ugo, double &vgo, bool &masked)
+{
+    double lon = y[0], lat = y[1], ky = y[3];
+    bool err = (fabs(lat) >= HALFPI) || (fabs(ky) >= 100.0);  // wr.py:508-510
+    masked = err;
+    if (err) {
+        double n = qnan();
+        dy[0] = dy[1] = dy[2] = dy[3] = dy[4] = n;  // wr.py:552-553
+        ugo = vgo = n;
+        return;
+    }
+    Merc m = sample_mercator<FAST>(g, fb, lon, lat);
+    rhs_from_merc<FAST>(m, y, dy, ugo, vgo);
 }
 
 template <bool FAST>

@@ -12,8 +12,9 @@ struct RunParams;
 // rwrt_rk45_{fast,strict}.cu
 void launch_rk45_fast(const RunParams &p, int prepare_blocks, int fill_blocks, int integrate_blocks, cudaStream_t s);
 void launch_rk45_strict(const RunParams &p, int prepare_blocks, int fill_blocks, int integrate_blocks, cudaStream_t s);
-int occupancy_rk45_fast();
-int occupancy_rk45_strict();
+int occupancy_rk45_fast(bool coop);
+int occupancy_rk45_strict(bool coop);
+void launch_build_cells(const Grid &g, int nmember, double *fcell, cudaStream_t s);
 void launch_rhs_fast(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s);
 void launch_rhs_strict(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s);
 
@@ -44,7 +45,7 @@ void launch_grid_accumulate(long long nslot, int nt, const double *out7, double 
 int measure_fp64_peak(int sm_count, double *tflops, cudaStream_t s);
 
 // rwrt_api.cu helpers
-void launch_compact_live(long long N, int nt, const double *out7, int32_t *live, unsigned long long *nlive_dev,
-                         int *block_counts, int nblocks, cudaStream_t s);
+void launch_compact_live(long long N, int nt, const double *out7, int nsource, int nzwn, int32_t *live,
+                         unsigned long long *nlive_dev, int *block_counts, int nblocks, cudaStream_t s);
 
 }  // namespace rwrt

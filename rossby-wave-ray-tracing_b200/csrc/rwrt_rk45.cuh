@@ -210,6 +210,12 @@ __constant__ double cC[7][6] = {
     {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
     {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
 
+// y + (sum_{j<s} K_j c_sj) * h for stage s with compile-time coefficient indices (constant-bank operands)
+#define RWRT_COMBO(S, EXPR)                          \
+    case S:                                          \
+        _Pragma("unroll") for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (EXPR) * h; \
+        break;
+
 // The integrator.  Persistent grid; every lane owns one ray at a time.  The six stages run through ONE
 // instance of the right-hand side (a loop, not six inlined copies): the kernel stays inside the
 // instruction cache (v2, fully unrolled, spent 27 % of its warp time on instruction-fetch stalls).
@@ -365,6 +371,285 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
     // warp-level reduction of the accepted-step total (the metric), one atomic per warp
     for (int o = 16; o > 0; o >>= 1) my_total += __shfl_down_sync(FULL, my_total, o);
     if (lane_id == 0 && my_total) atomicAdd(p.total_accepted, (unsigned long long)my_total);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Cooperative-gather integrator (the default when the handle holds a cell-major field table).
+//
+// v3 above is bound by the L1TEX wavefront pipe (profiles/r1_v3_*: 92 % of peak): every lane fetches
+// its own 4 corners x 96 B with 24 fully divergent LDG.128 per right-hand side.  Here the warp
+// fetches together: each ray's bilinear cell is ONE 384-byte record (11 fields x 4 corners, 3 cache
+// lines, line aligned), a quarter-warp copies one line of one ray with 8 contiguous 16-byte
+// cp.async (LDGSTS) -- 4 wavefronts per instruction instead of ~32 -- straight into a swizzled
+// shared-memory stage (no landing registers, all 24 copies of a stage in flight at once), and while
+// they fly the lanes evaluate sincos / the wavenumber reciprocals.  Each lane then reads its own
+// record back with conflict-free LDS.128.  Arithmetic and operation order are unchanged.
+// Shared memory per warp: 12 KB stage + 6.25 KB for K2..K6 -> 3 blocks of 128 threads per SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int CO_STAGE_BYTES = 32 * 384;                                   // per warp
+constexpr int CO_SMEM_BYTES = (RK_THREADS / 32) * CO_STAGE_BYTES + 5 * 5 * RK_THREADS * (int)sizeof(double);
+
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src));
+}
+
+__global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x;
+    const int lane_id = tid & 31, warp_id = tid >> 5;
+    unsigned char *stage = smem_raw + warp_id * CO_STAGE_BYTES;            // this warp's 32 x 384 B
+    double *ks = reinterpret_cast<double *>(smem_raw + (RK_THREADS / 32) * CO_STAGE_BYTES);
+    const unsigned stage_u32 = (unsigned)__cvta_generic_to_shared(stage);
+#define KS(s, c) ks[(((s) - 1) * 5 + (c)) * RK_THREADS + tid]            /* K2..K6 <-> s = 1..5 */
+    Lane L;
+    L.slot = -1;
+    double k1[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 5; ++c) L.y[c] = (c < 2) ? 0.0 : 1.0;              // benign state for idle lanes
+    L.h_abs = 1.0;
+    L.t = 0.0;
+    const double *fcb = p.g.fcell;
+    const double *fb = p.g.fpk;
+    bool queue_empty = false;
+    long long my_total = 0;
+    const int q8 = lane_id & 7, grp = lane_id >> 3;
+    // own-record read offsets: logical 16-byte chunk q of ray r lives at r*384 + (q>>3)*128 + ((q&7)^(r&7))*16
+    const unsigned char *my_rec = stage + lane_id * 384;
+    int swz[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) swz[j] = (j ^ (lane_id & 7)) << 4;
+
+    for (;;) {
+        __syncwarp();
+        // ---- refill idle lanes from the queue (one atomic per warp) ----
+        bool idle = (L.slot < 0);
+        unsigned idle_mask = __ballot_sync(FULL, idle);
+        if (idle_mask == FULL && queue_empty) break;
+        if (idle_mask != 0 && !queue_empty) {
+            int leader = __ffs(idle_mask) - 1;
+            unsigned long long base = 0;
+            if (lane_id == leader) base = atomicAdd(p.queue, (unsigned long long)__popc(idle_mask));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= (unsigned long long)p.nlive) queue_empty = true;
+            if (idle) {
+                unsigned long long mine = base + __popc(idle_mask & ((1u << lane_id) - 1));
+                if (mine < (unsigned long long)p.nlive) {
+                    const double *st = p.state + (size_t)mine * 12;
+                    L.slot = p.live[mine];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        L.y[c] = st[c];
+                        k1[c] = st[5 + c];
+                    }
+                    L.h_abs = st[10];
+                    L.t = 0.0;
+                    L.plon = L.y[0];
+                    L.plat = L.y[1];
+                    L.acc = 0;
+                    L.att = 0;
+                    L.it = 1;
+                    L.rejected = false;
+                    L.fresh = true;
+                    fb = member_base(p, L.slot);
+                    fcb = p.g.fcell + (fb - p.g.fpk) / p.g.member_stride * p.g.cell_member_stride;
+                }
+            }
+        }
+        const bool active = (L.slot >= 0);
+
+        // ---- one attempt (rkf45.py:410-502); idle lanes run along on a benign state (they serve the gathers) ----
+        double tb = L.it * p.tstep;  // wr.py:798-801
+        if (L.it == p.nt - 1 && tb > p.ttotal) tb = p.ttotal;
+        if (active && L.fresh) {  // rkf45.py:383-387, once per pass
+            if (!(L.h_abs >= p.gmin) && L.h_abs == L.h_abs) L.h_abs = p.gmin;
+            L.rejected = false;
+            L.fresh = false;
+        }
+        double t_new = L.t + L.h_abs;  // rkf45.py:426-435
+        if (t_new - tb > 0) t_new = tb;
+        const double h = active ? (t_new - L.t) : 0.0;
+        double ys[5], kn[5], ug = 0, vg = 0;
+        bool masked = false;
+#pragma unroll 1
+        for (int s = 1; s <= 6; ++s) {
+            // rkf45.py:306-311 / 316: y + (sum_{j<s} K_j c_sj) * h, the sum accumulated in j order
+            switch (s) {
+                RWRT_COMBO(1, k1[c] * cC[1][0])
+                RWRT_COMBO(2, k1[c] * cC[2][0] + KS(1, c) * cC[2][1])
+                RWRT_COMBO(3, k1[c] * cC[3][0] + KS(1, c) * cC[3][1] + KS(2, c) * cC[3][2])
+                RWRT_COMBO(4, k1[c] * cC[4][0] + KS(1, c) * cC[4][1] + KS(2, c) * cC[4][2] + KS(3, c) * cC[4][3])
+                RWRT_COMBO(5, k1[c] * cC[5][0] + KS(1, c) * cC[5][1] + KS(2, c) * cC[5][2] + KS(3, c) * cC[5][3] +
+                                  KS(4, c) * cC[5][4])
+                default:
+#pragma unroll
+                    for (int c = 0; c < 5; ++c)
+                        ys[c] = L.y[c] + (k1[c] * cC[6][0] + KS(1, c) * cC[6][1] + KS(2, c) * cC[6][2] +
+                                          KS(3, c) * cC[6][3] + KS(4, c) * cC[6][4] + KS(5, c) * cC[6][5]) * h;
+                    break;
+            }
+            // phase A: which cell, which weights (interpolation.py:77-85, 112-130)
+            const double lon = ys[0], lat = ys[1];
+            const bool inr = fabs(lat) <= HALFPI;                         // bs.py:787
+            int x0, y0, x1, y1;
+            double sx, sy;
+            locate<RWRT_FAST>(p.g, lon, inr ? lat : 0.0, x0, y0, x1, y1, sx, sy);
+            const double *rec = fcb + ((size_t)x0 * p.g.nlat + y0) * NCELL;
+            // cooperative copy: quarter-warp `grp` copies ray 4g+grp, lane q8 moves chunk q8 of each of its 3 lines
+            __syncwarp();                                                  // previous stage's reads are done
+#pragma unroll
+            for (int g8 = 0; g8 < 8; ++g8) {
+                const int r = 4 * g8 + grp;
+                const unsigned long long src = __shfl_sync(FULL, (unsigned long long)rec, r);
+                const unsigned dst = stage_u32 + r * 384 + ((q8 ^ (r & 7)) << 4);
+                const char *sp = reinterpret_cast<const char *>(src) + (q8 << 4);
+                cp_async16(dst, sp);
+                cp_async16(dst + 128, sp + 128);
+                if (q8 < 6) cp_async16(dst + 256, sp + 256);              // chunks 22, 23 of a record are padding
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+            // work that does not need the fields, overlapped with the copies
+            const double wa = (1 - sx) * sy, wb = sx * sy, wc = (1 - sx) * (1 - sy), wd = sx * (1 - sy);
+            const bool err = (fabs(lat) >= HALFPI) || (fabs(ys[3]) >= 100.0);   // wr.py:508-510
+            const Trig tg = trig_of_lat<RWRT_FAST>(inr ? lat : 0.0);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncwarp();
+            // blend (interpolation.py:132-133): a*wa + b*wb + c*wc + d*wd, fields k = 0..10
+            double f[11];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) {
+                const int qa = 2 * k, qc = 2 * k + 1;
+                const double2 ab = *reinterpret_cast<const double2 *>(my_rec + (qa >> 3) * 128 + swz[qa & 7]);
+                const double2 cd = *reinterpret_cast<const double2 *>(my_rec + (qc >> 3) * 128 + swz[qc & 7]);
+                f[k] = ab.x * wa + ab.y * wb + cd.x * wc + cd.y * wd;
+            }
+            masked = err;
+            if (err || !inr) {
+                const double n = qnan();
+#pragma unroll
+                for (int c = 0; c < 5; ++c) kn[c] = n;                     // wr.py:552-553 / bs.py:787
+                ug = vg = n;
+            } else {
+                Merc m = mercator_from_fields<RWRT_FAST>(f, tg);
+                rhs_from_merc<RWRT_FAST>(m, ys, kn, ug, vg);
+            }
+            if (s < 6) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) KS(s, c) = kn[c];
+            }
+        }
+        if (!active) continue;
+        ++L.att;
+        // now ys = y_new and kn = f(y_new) (rkf45.py:317-319)
+        double r[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {  // rkf45.py:442-446
+            double scale = p.atol + np_maximum(fabs(L.y[c]), fabs(ys[c])) * p.rtol;
+            double e = k1[c] * E1 + KS(1, c) * E2 + KS(2, c) * E3 + KS(3, c) * E4 + KS(4, c) * E5 + KS(5, c) * E6 +
+                       kn[c] * E7;
+            r[c] = (h * e) / scale;
+        }
+        double err = rms5(r[0], r[1], r[2], r[3], r[4]);
+        if (err != err) err = 0;
+        const bool accept = err < 1;
+        double factor = step_factor(err, accept);
+        if (accept) {
+            if (L.rejected && factor > 1.0) factor = 1.0;  // rkf45.py:462-469
+        } else {
+            L.rejected = true;
+        }
+        L.h_abs = fabs(h) * factor;
+        if (!accept) continue;
+
+        // ---- accepted step ----
+        ++L.acc;
+        L.t = (t_new != t_new) ? tb : t_new;  // rkf45.py:503
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            L.y[c] = ys[c];
+            k1[c] = kn[c];  // FSAL: f(y_new) is the next pass's self.f (rkf45.py:378 recomputes the same value)
+        }
+        L.fresh = true;
+        double ysum = L.y[0] + L.y[1] + L.y[2] + L.y[3] + L.y[4];  // np.mean(y) is NaN (rkf45.py:400-402)
+        bool dead = (ysum != ysum);
+        if (!dead && L.t != tb) continue;
+
+        // ---- output time reached (wr.py:831-885) ----
+        int code = 1;  // RWRT_RAY_ALIVE
+        if (dead) code = 4;
+        if (fabs(L.y[1]) >= HALFPI) {  // wr.py:838-843
+            dead = true;
+            code = 2;
+        }
+        if (!dead) {
+            double dd = haversine(L.y[0], L.y[1], L.plon, L.plat);  // wr.py:844-850
+            if (fabs(dd) >= p.cut) {
+                dead = true;
+                code = 3;
+            }
+        }
+        if (dead) {
+            double n = qnan();
+            for (int it = L.it; it < p.nt; ++it) write_row(p, L.slot, it, n, n, n, n, n, n, n);
+        } else {
+            // wr.py:856-865: ug, vg at the output point = what the last stage evaluated at y_new
+            if (masked) {
+                double2 gv = output_ugvg_slow(p.g, fb, L.y[0], L.y[1], L.y[2], L.y[3]);
+                ug = gv.x;
+                vg = gv.y;
+            }
+            write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
+            L.plon = L.y[0];
+            L.plat = L.y[1];
+            ++L.it;
+        }
+        if (dead || L.it >= p.nt) {  // ray finished: publish counters, free the lane
+            if (p.accepted) p.accepted[L.slot] = L.acc;
+            if (p.attempts) p.attempts[L.slot] = L.att;
+            if (p.status) p.status[L.slot] = (signed char)code;
+            my_total += L.acc;
+            L.slot = -1;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                L.y[c] = (c < 2) ? 0.0 : 1.0;
+                k1[c] = 0.0;
+            }
+            L.h_abs = 1.0;
+            L.t = 0.0;
+            L.it = 1;
+        }
+    }
+#undef KS
+    for (int o = 16; o > 0; o >>= 1) my_total += __shfl_down_sync(FULL, my_total, o);
+    if (lane_id == 0 && my_total) atomicAdd(p.total_accepted, (unsigned long long)my_total);
+}
+
+// Cell-major table: record (x0, y0) = for k in 0..10: a = F[x0][y1], b = F[x1][y1], c = F[x0][y0], d = F[x1][y0]
+// with x1 = min(x0+1, W-1), y1 = min(y0+1, H-1) (the clamps of interpolation.py:116-119 baked in).
+__global__ void __launch_bounds__(256) build_cells_kernel(Grid g, int nmember, double *fcell)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = g.nlon_f, H = g.nlat;
+    size_t ncell = (size_t)nmember * W * H;
+    if (i >= ncell) return;
+    int y0 = (int)(i % H);
+    size_t t = i / H;
+    int x0 = (int)(t % W), m = (int)(t / W);
+    int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    const double *fb = g.fpk + (size_t)m * g.member_stride;
+    const double *pa = fb + ((size_t)x0 * H + y1) * NPK, *pb = fb + ((size_t)x1 * H + y1) * NPK;
+    const double *pc = fb + ((size_t)x0 * H + y0) * NPK, *pd = fb + ((size_t)x1 * H + y0) * NPK;
+    double *o = fcell + i * NCELL;
+    for (int k = 0; k < 11; ++k) {
+        o[4 * k + 0] = pa[k];
+        o[4 * k + 1] = pb[k];
+        o[4 * k + 2] = pc[k];
+        o[4 * k + 3] = pd[k];
+    }
+    for (int k = 44; k < NCELL; ++k) o[k] = 0.0;
 }
 
 }  // namespace RWRT_VARIANT

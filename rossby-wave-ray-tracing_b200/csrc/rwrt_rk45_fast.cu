@@ -10,12 +10,20 @@ void launch_rk45_fast(const RunParams &p, int prepare_blocks, int fill_blocks, i
     if (p.N > 0 && p.nt > 1) fast::fill_static_slots<<<dim3(fill_blocks, p.nt - 1), 256, 0, s>>>(p);
     if (p.nlive > 0) {
         fast::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
-        fast::rk45_integrate<<<integrate_blocks, fast::RK_THREADS, fast::RK_SMEM_BYTES, s>>>(p);
+        if (p.g.fcell)
+            fast::rk45_integrate_coop<<<integrate_blocks, fast::RK_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
+        else
+            fast::rk45_integrate<<<integrate_blocks, fast::RK_THREADS, fast::RK_SMEM_BYTES, s>>>(p);
     }
 }
-int occupancy_rk45_fast()
+int occupancy_rk45_fast(bool coop)
 {
     int nb = 0;
+    if (coop) {
+        cudaFuncSetAttribute(fast::rk45_integrate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::CO_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast::rk45_integrate_coop, fast::RK_THREADS, fast::CO_SMEM_BYTES);
+        return nb;
+    }
     cudaFuncSetAttribute(fast::rk45_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RK_SMEM_BYTES);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast::rk45_integrate, fast::RK_THREADS, fast::RK_SMEM_BYTES);
     return nb;
@@ -33,5 +41,10 @@ __global__ void rhs_kernel_fast(Grid g, long long n, const double *y, const int3
 void launch_rhs_fast(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s)
 {
     if (n > 0) rhs_kernel_fast<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, n, y, member, dy);
+}
+void launch_build_cells(const Grid &g, int nmember, double *fcell, cudaStream_t s)
+{
+    size_t ncell = (size_t)nmember * g.nlon_f * g.nlat;
+    fast::build_cells_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(g, nmember, fcell);
 }
 }  // namespace rwrt

@@ -10,12 +10,20 @@ void launch_rk45_strict(const RunParams &p, int prepare_blocks, int fill_blocks,
     if (p.N > 0 && p.nt > 1) strict::fill_static_slots<<<dim3(fill_blocks, p.nt - 1), 256, 0, s>>>(p);
     if (p.nlive > 0) {
         strict::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
-        strict::rk45_integrate<<<integrate_blocks, strict::RK_THREADS, strict::RK_SMEM_BYTES, s>>>(p);
+        if (p.g.fcell)
+            strict::rk45_integrate_coop<<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
+        else
+            strict::rk45_integrate<<<integrate_blocks, strict::RK_THREADS, strict::RK_SMEM_BYTES, s>>>(p);
     }
 }
-int occupancy_rk45_strict()
+int occupancy_rk45_strict(bool coop)
 {
     int nb = 0;
+    if (coop) {
+        cudaFuncSetAttribute(strict::rk45_integrate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::CO_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, strict::rk45_integrate_coop, strict::RK_THREADS, strict::CO_SMEM_BYTES);
+        return nb;
+    }
     cudaFuncSetAttribute(strict::rk45_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::RK_SMEM_BYTES);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, strict::rk45_integrate, strict::RK_THREADS, strict::RK_SMEM_BYTES);
     return nb;
