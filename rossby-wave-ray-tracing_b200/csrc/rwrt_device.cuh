@@ -115,15 +115,17 @@ struct Merc {
 
 // cos / sin / tan of the latitude as bs.py:856-857, 876-877 evaluate them (FAST: one sincos and a division)
 struct Trig {
-    double cp, sp, tl;
+    double cp, sp, tl, rc;  // rc = 1/cos (FAST only)
 };
 template <bool FAST>
 __device__ __forceinline__ Trig trig_of_lat(double lat)
 {
     Trig t;
+    t.rc = 0.0;
     if (FAST) {
         sincos(lat, &t.sp, &t.cp);
-        t.tl = t.sp / t.cp;
+        t.rc = 1.0 / t.cp;
+        t.tl = t.sp * t.rc;
     } else {
         t.cp = cos(lat);
         t.sp = sin(lat);
@@ -158,7 +160,7 @@ __device__ __forceinline__ Merc mercator_from_fields(const double *f, const Trig
     m.uy = fuy + tl * fu;
     m.vy = fvy + tl * fv;
     if (FAST) {
-        double rc = 1.0 / cp;
+        const double rc = tg.rc;
         m.ux = fux * rc;
         m.vx = fvx * rc;
         m.u = fu * rc;
@@ -220,20 +222,33 @@ __device__ __forceinline__ void ugvg_numpy(double fu, double fv, double fqx, dou
 // FAST: same formulas with the shared denominators inverted once (1 reciprocal instead of 7 divisions
 // in the wavenumber algebra, multiplication by 1/a instead of 5 divisions) -- differences are at the
 // level of one rounding per operation, like FMA contraction.
+// FAST build: everything the ray equations need from (k, l) alone, so that it can be evaluated while
+// the field gather is still in flight.
+struct WaveRecip {
+    double kap, kap2, rkk, rkap1, rden;
+};
+__device__ __forceinline__ WaveRecip wave_recip(double kx, double ky)
+{
+    WaveRecip w;
+    double k2 = kx * kx, l2 = ky * ky;
+    double K2 = k2 + l2;                 // = kk = kx^2 (1 + kap^2)
+    double r = 1.0 / (kx * K2 * K2);     // one reciprocal for 1/kx, 1/kk, 1/kap1, 1/(kk kap1)
+    double rk = r * K2 * K2;             // 1/kx
+    w.kap = ky * rk;
+    w.kap2 = w.kap * w.kap;
+    w.rkk = r * kx * K2;                 // 1/kk
+    w.rkap1 = k2 * w.rkk;                // 1/kap1 = kx^2 / kk
+    w.rden = w.rkk * w.rkap1;            // 1/(kk kap1)
+    return w;
+}
+
 template <bool FAST>
-__device__ __forceinline__ void rhs_from_merc(const Merc &m, const double *y, double *dy, double &ugo, double &vgo)
+__device__ __forceinline__ void rhs_from_merc(const Merc &m, const double *y, const WaveRecip &w, double *dy,
+                                              double &ugo, double &vgo)
 {
     double kx = y[2], ky = y[3], amp = y[4];
     if (FAST) {
-        double k2 = kx * kx, l2 = ky * ky;
-        double K2 = k2 + l2;                 // = kk = kx^2 (1 + kap^2)
-        double r = 1.0 / (kx * K2 * K2);     // one reciprocal for 1/kx, 1/kk, 1/kap1, 1/(kk kap1)
-        double rk = r * K2 * K2;             // 1/kx
-        double kap = ky * rk;
-        double kap2 = kap * kap;
-        double rkk = r * kx * K2;            // 1/kk
-        double rkap1 = k2 * rkk;             // 1/kap1 = kx^2 / kk
-        double rden = rkk * rkap1;           // 1/(kk kap1)
+        const double kap = w.kap, kap2 = w.kap2, rkk = w.rkk, rkap1 = w.rkap1, rden = w.rden;
         double ug = m.u + (((1. - kap2) * m.qy) - (2. * kap * m.qx)) * rden;
         double vg = m.v + ((2. * kap * m.qy) + ((1. - kap2) * m.qx)) * rden;
         double dzwn = -kx * ((m.ux + kap * m.vx) + (kap * m.qxx - m.qyx) * rkk);
@@ -290,7 +305,9 @@ __device__ __forceinline__ void ray_rhs(const Grid &g, const double *__restrict_
         return;
     }
     Merc m = sample_mercator<FAST>(g, fb, lon, lat);
-    rhs_from_merc<FAST>(m, y, dy, ugo, vgo);
+    WaveRecip w;
+    if (FAST) w = wave_recip(y[2], ky);
+    rhs_from_merc<FAST>(m, y, w, dy, ugo, vgo);
 }
 
 template <bool FAST>
@@ -309,6 +326,18 @@ __device__ __forceinline__ double haversine(double lon_c, double lat_c, double l
     double a = s1 * s1 + cos(lat_p) * cos(lat_c) * (s2 * s2);
     double c = 2 * atan2(sqrt(a), sqrt(1.0 - a));
     return fabs(c);
+}
+
+
+// FAST build of the speed cut-off test |2 atan2(sqrt a, sqrt(1-a))| >= cut (wr.py:97-112, 844-850):
+// the central angle is monotonic in a on [0, pi], so compare a with sin^2(cut/2); cos of both latitudes
+// are already known (cos_c from the last stage, cos_p cached from the previous output).
+__device__ __forceinline__ bool speed_cutoff_fast(double lon_c, double lat_c, double lon_p, double lat_p, double cos_c,
+                                                  double cos_p, double sin2_half_cut)
+{
+    double s1 = sin((lat_c - lat_p) / 2.0), s2 = sin((lon_c - lon_p) / 2.0);
+    double a = s1 * s1 + cos_p * cos_c * (s2 * s2);
+    return a >= sin2_half_cut;
 }
 
 }  // namespace rwrt

@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
     bool queue_empty = false;
     long long my_total = 0;
     const int q8 = lane_id & 7, grp = lane_id >> 3;
+    double pcos = 1.0;                                                     // cos(latitude of the previous output)
+    const double shc = sin(0.5 * p.cut), sin2_half_cut = (p.cut >= PI) ? 2.0 : shc * shc;  // angle <= pi: never cut
     // own-record read offsets: logical 16-byte chunk q of ray r lives at r*384 + (q>>3)*128 + ((q&7)^(r&7))*16
     const unsigned char *my_rec = stage + lane_id * 384;
     int swz[8];
@@ -449,6 +451,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
                     L.t = 0.0;
                     L.plon = L.y[0];
                     L.plat = L.y[1];
+                    pcos = cos(L.plat);
                     L.acc = 0;
                     L.att = 0;
                     L.it = 1;
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
         double t_new = L.t + L.h_abs;  // rkf45.py:426-435
         if (t_new - tb > 0) t_new = tb;
         const double h = active ? (t_new - L.t) : 0.0;
-        double ys[5], kn[5], ug = 0, vg = 0;
+        double ys[5], kn[5], ug = 0, vg = 0, cos_new = 1.0;
         bool masked = false;
 #pragma unroll 1
         for (int s = 1; s <= 6; ++s) {
@@ -515,6 +518,8 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             const double wa = (1 - sx) * sy, wb = sx * sy, wc = (1 - sx) * (1 - sy), wd = sx * (1 - sy);
             const bool err = (fabs(lat) >= HALFPI) || (fabs(ys[3]) >= 100.0);   // wr.py:508-510
             const Trig tg = trig_of_lat<RWRT_FAST>(inr ? lat : 0.0);
+            WaveRecip wr;
+            if (RWRT_FAST) wr = wave_recip(ys[2], ys[3]);
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncwarp();
             // blend (interpolation.py:132-133): a*wa + b*wb + c*wc + d*wd, fields k = 0..10
@@ -534,7 +539,8 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
                 ug = vg = n;
             } else {
                 Merc m = mercator_from_fields<RWRT_FAST>(f, tg);
-                rhs_from_merc<RWRT_FAST>(m, ys, kn, ug, vg);
+                rhs_from_merc<RWRT_FAST>(m, ys, wr, kn, ug, vg);
+                cos_new = tg.cp;
             }
             if (s < 6) {
 #pragma unroll
@@ -585,8 +591,14 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             code = 2;
         }
         if (!dead) {
-            double dd = haversine(L.y[0], L.y[1], L.plon, L.plat);  // wr.py:844-850
-            if (fabs(dd) >= p.cut) {
+            bool too_fast;
+            if (RWRT_FAST && !masked) {
+                too_fast = speed_cutoff_fast(L.y[0], L.y[1], L.plon, L.plat, cos_new, pcos, sin2_half_cut);
+            } else {
+                double dd = haversine(L.y[0], L.y[1], L.plon, L.plat);  // wr.py:844-850
+                too_fast = fabs(dd) >= p.cut;
+            }
+            if (too_fast) {
                 dead = true;
                 code = 3;
             }
@@ -604,6 +616,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
             L.plon = L.y[0];
             L.plat = L.y[1];
+            pcos = masked ? cos(L.y[1]) : cos_new;
             ++L.it;
         }
         if (dead || L.it >= p.nt) {  // ray finished: publish counters, free the lane
