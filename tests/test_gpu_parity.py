@@ -262,3 +262,105 @@ def test_poles_and_speed_cutoff_termination():
     assert (died_ref == died_gpu).mean() > 0.97
     assert set(np.unique(w.status)).issubset({0, 1, 2, 3, 4})
     assert ((w.status == lib.RAY_ALIVE) == (~np.isnan(w.rlon[-1]) & live)).all()
+
+
+def test_ensemble_members_match_single_runs():
+    """BASELINE configs[3] in miniature: an ensemble of background states batched in one handle
+    (nmember > 1, per-source member index) gives, bit for bit, what separate single-member runs give."""
+    import torch
+    members = [synthetic.ensemble_member(e, 144, 73) for e in range(3)]
+    lon, lat = synthetic.grid_coords(144, 73)
+    sl, sa = synthetic.random_sources(30, 9)
+    slon, slat = np.radians(sl), np.radians(sa)
+    zwn = np.array([1.0, 3.0])
+    days, nt = 6.0, 73
+    member_of = np.arange(30, dtype=np.int32) % 3
+    L = lib.load()
+    h = lib.vp()
+    lib.check(L.rwrt_create(0, 144, 73, 1, 3, C.byref(h)))
+    dev = torch.device("cuda", 0)
+    U = torch.from_numpy(np.stack([m[0] for m in members])).to(dev)
+    V = torch.from_numpy(np.stack([m[1] for m in members])).to(dev)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
+         dict(lon=lon, lat=lat, cl=np.cos(lat), sl=np.sin(lat), slon=slon, slat=slat, zwn=zwn, mem=member_of).items()}
+    lib.check(L.rwrt_bs_ready(h, lib.ptr(U), lib.ptr(V), lib.ptr(d["lon"]), lib.ptr(d["lat"]), lib.ptr(d["cl"]),
+                              lib.ptr(d["sl"]), None, None, lib.stream_ptr()))
+    N = 3 * 30 * 2
+    out = torch.empty((7, nt, N), dtype=torch.float64, device=dev)
+    acc = torch.zeros(N, dtype=torch.int64, device=dev)
+    lib.check(L.rwrt_ray_init(h, 30, lib.ptr(d["slon"]), lib.ptr(d["slat"]), lib.ptr(d["mem"]), 2, lib.ptr(d["zwn"]),
+                              0.0, nt, lib.ptr(out), lib.stream_ptr()))
+    lib.check(L.rwrt_ray_run_rk45(h, 30, lib.ptr(d["mem"]), 2, nt, 7200.0, days * 86400.0, 1e-6, 1e-6, 1e-3, 0.1,
+                                  lib.MODE_FAST, lib.ptr(out), lib.ptr(acc), None, None, None, lib.stream_ptr()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(7, nt, 3, 30, 2)
+    got_acc = acc.cpu().numpy().reshape(3, 30, 2)
+    L.rwrt_destroy(h)
+    for e in range(3):
+        idx = np.where(member_of == e)[0]
+        w = make_wr(members[e][0], members[e][1], zwn, slon[idx], slat[idx], days)
+        w.ray_run(mode="numpy", inte_method="rk45")
+        for k, n in enumerate(parity.NAMES):
+            assert np.array_equal(got[k][:, :, idx, :], getattr(w, n), equal_nan=True), (e, n)
+        assert np.array_equal(got_acc[:, idx, :], w.accepted)
+
+
+def test_quarter_degree_grid_point_major_kernel():
+    """BASELINE configs[4] in miniature: 0.25-degree grid (cell table would be 399 MB -> the point-major
+    kernel is used), a few hundred sources, against the oracle on its non-grazing set; also checks that
+    the two integrators (cooperative cell gather / per-lane point gather) agree bit for bit on a 1-degree case."""
+    import os
+    u, v = synthetic.clim(1440, 721)
+    sl, sa = synthetic.random_sources(120, 123)
+    slon, slat = np.radians(sl), np.radians(sa)
+    zwn = np.array([2.0, 4.0])
+    ref, acc, ng = parity.oracle_nongrazing(u, v, slon, slat, zwn, 6.0)
+    w = make_wr(u, v, zwn, slon, slat, 6.0)
+    w.ray_run(mode="numpy", inte_method="rk45", strict=True)
+    got = {n: getattr(w, n) for n in parity.NAMES}
+    st = parity.compare(got, w.accepted, ref, acc, ng, "quarter-degree")
+    assert st["nongrazing"] > 0.5 * st["live"]
+    # same rays through both kernels on a grid where both exist
+    u2, v2 = synthetic.clim(360, 181)
+    w1 = make_wr(u2, v2, zwn, slon, slat, 6.0)
+    w1.ray_run(mode="numpy", inte_method="rk45", strict=True)
+    os.environ["RWRT_CELL_LIMIT_MB"] = "0"
+    try:
+        w2 = make_wr(u2, v2, zwn, slon, slat, 6.0)
+        w2.ray_run(mode="numpy", inte_method="rk45", strict=True)
+    finally:
+        del os.environ["RWRT_CELL_LIMIT_MB"]
+    for n in parity.NAMES:
+        assert np.array_equal(getattr(w1, n), getattr(w2, n), equal_nan=True), n
+    assert np.array_equal(w1.accepted, w2.accepted)
+
+
+def test_frequency_sweep_with_gridding():
+    """BASELINE configs[2] in miniature: periods inf / 50 / 30 / 20 days x k = 1..8 from a source matrix,
+    gridded ray counts bit-exact against the NumPy definition; omega enters only the t = 0 cubic (bs.py:1005)."""
+    from rwrt_b200 import gridding
+    from oracle import gridding as ogrid
+    u, v = synthetic.clim(360, 181)
+    zwn = np.arange(1.0, 9.0)
+    total = None
+    first_l0 = None
+    for period in (np.inf, 50.0, 30.0, 20.0):
+        freq = 0.0 if np.isinf(period) else 2 * np.pi / (period * 86400.0)
+        w = WR(8, 100, 7200.0, 6 * 86400.0, freq, nx=360, ny=181)
+        w.bs.lon, w.bs.lat = synthetic.grid_coords(360, 181)
+        w.bs.u, w.bs.v = u, v
+        w.bs.ready(xcyclic=True)
+        w.set_zwn(zwn)
+        w.set_source_matrix(0.0, -49.5, 36.0, 10.0, 10, 10)
+        w.ray_run(mode="numpy", inte_method="rk45")
+        grids = gridding.accumulate(w, 2.0, 2.0)
+        out7 = np.stack([getattr(w, n) for n in parity.NAMES])
+        ref = ogrid.accumulate(out7, 2.0, 2.0)
+        for g, r in zip(grids, ref):
+            assert np.array_equal(g.cpu().numpy(), r)
+        if first_l0 is None:
+            first_l0 = w.rmwn[0].copy()
+        else:
+            assert not np.array_equal(first_l0, w.rmwn[0], equal_nan=True)   # omega changes the roots
+        total = ref[0] if total is None else total + ref[0]
+    assert total.sum() > 1e5
