@@ -113,6 +113,51 @@ struct Merc {
     double cosl, sinl;
 };
 
+// FAST-build math: branch-free sin/cos for |x| <= pi/2 (one quadrant fold by Cody-Waite, then the fdlibm
+// kernel polynomials on [-pi/4, pi/4]; < 1 ulp), with the coefficients as constant-bank operands.  The
+// library sincos costs 12 % of the integrator's instructions (slow-path branch, coefficient table loads).
+__constant__ double cSinCos[12] = {
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+
+__device__ __forceinline__ void sincos_halfpi(double x, double &sn, double &cs)
+{
+    const double q = rint(x * 0.63661977236758134308);            // -1, 0 or 1 for |x| <= pi/2
+    double r = fma(-q, 1.57079632679489655800e+00, x);
+    r = fma(-q, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = fma(z, cSinCos[5], cSinCos[4]);
+    double pc = fma(z, cSinCos[11], cSinCos[10]);
+    ps = fma(z, ps, cSinCos[3]);
+    pc = fma(z, pc, cSinCos[9]);
+    ps = fma(z, ps, cSinCos[2]);
+    pc = fma(z, pc, cSinCos[8]);
+    ps = fma(z, ps, cSinCos[1]);
+    pc = fma(z, pc, cSinCos[7]);
+    ps = fma(z, ps, cSinCos[0]);
+    pc = fma(z, pc, cSinCos[6]);
+    const double sr = fma(r * z, ps, r);                           // sin(r)
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));          // cos(r)
+    sn = (q == 0.0) ? sr : ((q > 0.0) ? cr : -cr);
+    cs = (q == 0.0) ? cr : ((q > 0.0) ? -sr : sr);
+}
+
+// FAST-build err^(-1/5) for the step controller (rkf45.py:453-455, 474-475): float seed + two Newton
+// steps y <- y (6 - a y^5) / 5 in double (quadratic: 2^-21 -> 2^-42 -> full), instead of the 166-instruction pow().
+__device__ __forceinline__ double pow_m02(double a)
+{
+    double y = (double)exp2f(-0.2f * __log2f((float)a));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        double y2 = y * y;
+        double y5 = y2 * y2 * y;
+        y = y * (fma(-a, y5, 6.0) * 0.2);
+    }
+    return y;
+}
+
 // cos / sin / tan of the latitude as bs.py:856-857, 876-877 evaluate them (FAST: one sincos and a division)
 struct Trig {
     double cp, sp, tl, rc;  // rc = 1/cos (FAST only)
@@ -123,7 +168,7 @@ __device__ __forceinline__ Trig trig_of_lat(double lat)
     Trig t;
     t.rc = 0.0;
     if (FAST) {
-        sincos(lat, &t.sp, &t.cp);
+        sincos_halfpi(lat, t.sp, t.cp);
         t.rc = 1.0 / t.cp;
         t.tl = t.sp * t.rc;
     } else {

@@ -120,24 +120,29 @@ __global__ void __launch_bounds__(128) rk45_prepare(RunParams p)
 __global__ void __launch_bounds__(256) fill_static_slots(RunParams p)
 {
     long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int it = blockIdx.y + 1;
-    if (slot >= p.N || it >= p.nt) return;
+    if (slot >= p.N) return;
     const size_t pl = (size_t)p.nt * p.N;
-    double s = p.out[0 * pl + slot] + p.out[1 * pl + slot] + p.out[2 * pl + slot] + p.out[3 * pl + slot] +
-               p.out[4 * pl + slot];
+    double v0 = p.out[0 * pl + slot], v1 = p.out[1 * pl + slot], v2 = p.out[2 * pl + slot], v3 = p.out[3 * pl + slot],
+           v4 = p.out[4 * pl + slot];
+    double s = v0 + v1 + v2 + v3 + v4;
     if (s == s) return;  // live slot: written by the integrator
-    size_t o = (size_t)it * p.N + slot;
-    double n = qnan();
-    // rays whose lon/lat/k are themselves NaN propagate that NaN; reference does the same
-    p.out[0 * pl + o] = p.out[0 * pl + slot];
-    p.out[1 * pl + o] = p.out[1 * pl + slot];
-    p.out[2 * pl + o] = p.out[2 * pl + slot];
-    p.out[3 * pl + o] = p.out[3 * pl + slot];  // NaN root stays NaN; a finite l with NaN A stays as it is
-    p.out[4 * pl + o] = p.out[4 * pl + slot];
-    // ug, vg at outputs: fresh sample + extent form (wr.py:856-865); NaN because l or the state is NaN
-    p.out[5 * pl + o] = n;
-    p.out[6 * pl + o] = n;
-    if (it == 1) {
+    const double n = qnan();
+    // this block's share of the output rows (gridDim.y chunks); consecutive threads write consecutive slots
+    int per = (p.nt - 1 + gridDim.y - 1) / gridDim.y;
+    int it0 = 1 + blockIdx.y * per, it1 = min(p.nt, it0 + per);
+    for (int it = it0; it < it1; ++it) {
+        size_t o = (size_t)it * p.N + slot;
+        // the t=0 values stay (NaN root stays NaN, a NaN position stays NaN): the reference never advances such a slot
+        p.out[0 * pl + o] = v0;
+        p.out[1 * pl + o] = v1;
+        p.out[2 * pl + o] = v2;
+        p.out[3 * pl + o] = v3;
+        p.out[4 * pl + o] = v4;
+        // ug, vg at outputs: fresh sample + extent form (wr.py:856-865); NaN because l or the state is NaN
+        p.out[5 * pl + o] = n;
+        p.out[6 * pl + o] = n;
+    }
+    if (blockIdx.y == 0) {
         if (p.accepted) p.accepted[slot] = 0;
         if (p.attempts) p.attempts[slot] = 0;
         if (p.status) p.status[slot] = 0;
@@ -178,13 +183,14 @@ __device__ __forceinline__ void write_row(const RunParams &p, long long slot, in
 // outside (5e-6, 2000): there the clipped value does not depend on pow's rounding.
 __device__ __forceinline__ double step_factor(double err, bool accept)
 {
+    // one evaluation site for the power (it is an out-of-line 166-instruction routine in the strict build)
+    double f = 0.0;
+    if (err >= 5.0e-6 && err <= 2000.0) f = 0.9 * (RWRT_FAST ? pow_m02(err) : pow(err, -0.2));
     if (accept) {
         if (err < 5.0e-6) return 10.0;  // 0.9 * err^-0.2 > 10.3 (also err == 0, rkf45.py:455)
-        double f = 0.9 * pow(err, -0.2);
         return f < 10.0 ? f : 10.0;
     }
     if (err > 2000.0) return 0.2;       // 0.9 * err^-0.2 < 0.197
-    double f = 0.9 * pow(err, -0.2);
     return f > 0.2 ? f : 0.2;
 }
 

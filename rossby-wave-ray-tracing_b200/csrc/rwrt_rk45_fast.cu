@@ -7,7 +7,7 @@
 namespace rwrt {
 void launch_rk45_fast(const RunParams &p, int prepare_blocks, int fill_blocks, int integrate_blocks, cudaStream_t s)
 {
-    if (p.N > 0 && p.nt > 1) fast::fill_static_slots<<<dim3(fill_blocks, p.nt - 1), 256, 0, s>>>(p);
+    if (p.N > 0 && p.nt > 1) fast::fill_static_slots<<<dim3(fill_blocks, p.nt - 1 < 8 ? p.nt - 1 : 8), 256, 0, s>>>(p);
     if (p.nlive > 0) {
         fast::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
         if (p.g.fcell)
