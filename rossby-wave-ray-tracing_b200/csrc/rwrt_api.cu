@@ -68,7 +68,8 @@ struct rwrt_ctx {
     double lon0 = 0, dlon = 0, lat0 = 0, dlat = 0;
     DevBuf fpk, fcell, scratch, trig, live, state, counters, blockcnt;
     bool have_cells = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux = nullptr;  // side stream for work that is independent of the integrator
     bool timed = false;
     double last_launches = 0, last_nlive = 0;
 
@@ -256,6 +257,13 @@ int rwrt_create(int device, int nlon, int nlat, int xcyclic, int nmember, rwrt_h
     }
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = numerically largest = lowest priority
+        CU(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, lo));
+    }
     *out = h;
     return RWRT_OK;
 }
@@ -274,6 +282,9 @@ int rwrt_destroy(rwrt_handle h)
     h->blockcnt.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->aux) cudaStreamDestroy(h->aux);
     delete h;
     return RWRT_OK;
 }
@@ -475,9 +486,13 @@ int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int
     int prepare_blocks = (int)(((long long)nlive + 127) / 128);
     int fill_blocks = (int)((N + 255) / 256);
     CU(cudaEventRecord(h->ev0, s));
-    if (strict) launch_rk45_strict(p, prepare_blocks, fill_blocks, integrate_blocks, s);
-    else launch_rk45_fast(p, prepare_blocks, fill_blocks, integrate_blocks, s);
+    CU(cudaEventRecord(h->ev_fork, s));            // fork: the side stream starts after everything queued so far
+    CU(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    if (strict) launch_rk45_strict(p, prepare_blocks, fill_blocks, integrate_blocks, s, h->aux);
+    else launch_rk45_fast(p, prepare_blocks, fill_blocks, integrate_blocks, s, h->aux);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_join, h->aux));       // join: the caller's stream continues after both are done
+    CU(cudaStreamWaitEvent(s, h->ev_join, 0));
     CU(cudaEventRecord(h->ev1, s));
     h->timed = true;
     h->last_launches = 3 + (nlive ? 3 : 1);  // compaction (3) + fill + prepare + integrate
