@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
     long long my_total = 0;
     const int q8 = lane_id & 7, grp = lane_id >> 3;
     double pcos = 1.0;                                                     // cos(latitude of the previous output)
+    const double *prev_rec = nullptr;                                      // cell record currently staged for this lane
     const double shc = sin(0.5 * p.cut), sin2_half_cut = (p.cut >= PI) ? 2.0 : shc * shc;  // angle <= pi: never cut
     // own-record read offsets: logical 16-byte chunk q of ray r lives at r*384 + (q>>3)*128 + ((q&7)^(r&7))*16
     const unsigned char *my_rec = stage + lane_id * 384;
@@ -507,17 +508,23 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             double sx, sy;
             locate<RWRT_FAST>(p.g, lon, inr ? lat : 0.0, x0, y0, x1, y1, sx, sy);
             const double *rec = fcb + ((size_t)x0 * p.g.nlat + y0) * NCELL;
+            // A ray often stays in the same cell from one stage to the next (stage times 0.8, 8/9, 1 of a step
+            // are close): its record is then still in this warp's stage buffer and is not fetched again.
+            const unsigned need_mask = __ballot_sync(FULL, rec != prev_rec);
+            prev_rec = rec;
             // cooperative copy: quarter-warp `grp` copies ray 4g+grp, lane q8 moves chunk q8 of each of its 3 lines
             __syncwarp();                                                  // previous stage's reads are done
 #pragma unroll
             for (int g8 = 0; g8 < 8; ++g8) {
                 const int r = 4 * g8 + grp;
                 const unsigned long long src = __shfl_sync(FULL, (unsigned long long)rec, r);
-                const unsigned dst = stage_u32 + r * 384 + ((q8 ^ (r & 7)) << 4);
-                const char *sp = reinterpret_cast<const char *>(src) + (q8 << 4);
-                cp_async16(dst, sp);
-                cp_async16(dst + 128, sp + 128);
-                if (q8 < 6) cp_async16(dst + 256, sp + 256);              // chunks 22, 23 of a record are padding
+                if ((need_mask >> r) & 1u) {
+                    const unsigned dst = stage_u32 + r * 384 + ((q8 ^ (r & 7)) << 4);
+                    const char *sp = reinterpret_cast<const char *>(src) + (q8 << 4);
+                    cp_async16(dst, sp);
+                    cp_async16(dst + 128, sp + 128);
+                    if (q8 < 6) cp_async16(dst + 256, sp + 256);          // chunks 22, 23 of a record are padding
+                }
             }
             asm volatile("cp.async.commit_group;\n" ::);
             // work that does not need the fields, overlapped with the copies
