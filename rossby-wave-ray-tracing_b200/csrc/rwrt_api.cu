@@ -548,21 +548,43 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
 {
     if (!h || !u || !v || !lon || !lat || !src_lon || !src_lat || !zwn || !out7_host)
         return fail(RWRT_ERR_ARG, "rwrt_real2d_host: NULL argument");
+    if (nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_real2d_host: bad sizes");
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaSetDevice(h->device));
     const size_t ng = (size_t)h->nmember * h->nlon * h->nlat;
-    const long long N = 3LL * nsource * nzwn;
-    const size_t nout = (size_t)7 * nt * N;
-    // one device arena for every input and output of the call
+    // The sources are processed in chunks: while chunk c integrates, the trajectories of chunk c-1 travel to
+    // the host on the copy stream (strided 2-D copies into the reference layout (7, nt, 3, nsource, nzwn)).
+    // Chunking is exact: a ray's result does not depend on its batch.
+    const size_t row_bytes_per_source = (size_t)nzwn * sizeof(double);
+    const size_t bytes_per_source = (size_t)7 * nt * 3 * row_bytes_per_source;
+    size_t target = (size_t)4 << 30;  // ~4 GB of trajectories per chunk
+    if (const char *e = getenv("RWRT_HOST_CHUNK_MB")) target = (size_t)strtoll(e, nullptr, 10) << 20;
+    int chunk = nsource;
+    if (bytes_per_source > 0 && (size_t)nsource * bytes_per_source > target + target / 2) {
+        chunk = (int)(target / bytes_per_source);
+        if (chunk < 1) chunk = 1;
+    }
+    const int nchunk = nsource > 0 ? (nsource + chunk - 1) / chunk : 0;
+    const long long Nc = 3LL * chunk * nzwn;
+    const size_t out_chunk = (size_t)7 * nt * Nc;
+    // one device arena for every input and the two chunk buffers
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     size_t o_u = carve(ng * 4), o_v = carve(ng * 4), o_lon = carve((size_t)h->nlon * 8), o_lat = carve((size_t)h->nlat * 8);
     size_t o_cl = carve((size_t)h->nlat * 8), o_sl = carve((size_t)h->nlat * 8);
     size_t o_slon = carve((size_t)nsource * 8), o_slat = carve((size_t)nsource * 8), o_mem = carve((size_t)nsource * 4);
-    size_t o_zwn = carve((size_t)nzwn * 8), o_acc = carve((size_t)N * 8), o_st = carve((size_t)N), o_tot = carve(8);
-    size_t o_out = carve(nout * 8);
+    size_t o_zwn = carve((size_t)nzwn * 8), o_tot = carve((size_t)(nchunk + 1) * 8);
+    size_t o_acc[2], o_st[2], o_out[2];
+    for (int b = 0; b < 2; ++b) {
+        o_acc[b] = carve((size_t)Nc * 8);
+        o_st[b] = carve((size_t)Nc);
+        o_out[b] = carve(out_chunk * 8);
+    }
     char *arena = nullptr;
     CU(cudaMalloc((void **)&arena, off));
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    int64_t *totals_host = nullptr;
     int rc = RWRT_OK;
 #define CUX(call)                                                                                       \
     do {                                                                                                \
@@ -572,6 +594,12 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
             goto done;                                                                                  \
         }                                                                                               \
     } while (0)
+    CUX(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CUX(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+        CUX(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+    }
+    CUX(cudaMallocHost((void **)&totals_host, (size_t)(nchunk + 1) * 8));
     CUX(cudaMemcpyAsync(arena + o_u, u, ng * 4, cudaMemcpyHostToDevice, s));
     CUX(cudaMemcpyAsync(arena + o_v, v, ng * 4, cudaMemcpyHostToDevice, s));
     CUX(cudaMemcpyAsync(arena + o_lon, lon, (size_t)h->nlon * 8, cudaMemcpyHostToDevice, s));
@@ -580,30 +608,65 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
         CUX(cudaMemcpyAsync(arena + o_cl, coslat, (size_t)h->nlat * 8, cudaMemcpyHostToDevice, s));
         CUX(cudaMemcpyAsync(arena + o_sl, sinlat, (size_t)h->nlat * 8, cudaMemcpyHostToDevice, s));
     }
-    CUX(cudaMemcpyAsync(arena + o_slon, src_lon, (size_t)nsource * 8, cudaMemcpyHostToDevice, s));
-    CUX(cudaMemcpyAsync(arena + o_slat, src_lat, (size_t)nsource * 8, cudaMemcpyHostToDevice, s));
-    if (src_member) CUX(cudaMemcpyAsync(arena + o_mem, src_member, (size_t)nsource * 4, cudaMemcpyHostToDevice, s));
-    CUX(cudaMemcpyAsync(arena + o_zwn, zwn, (size_t)nzwn * 8, cudaMemcpyHostToDevice, s));
-    {
-        const int32_t *dmem = src_member ? (const int32_t *)(arena + o_mem) : nullptr;
-        rc = rwrt_bs_ready(h, (const float *)(arena + o_u), (const float *)(arena + o_v), (const double *)(arena + o_lon),
-                           (const double *)(arena + o_lat), (coslat && sinlat) ? (const double *)(arena + o_cl) : nullptr,
-                           (coslat && sinlat) ? (const double *)(arena + o_sl) : nullptr, nullptr, nullptr, s);
-        if (rc) goto done;
-        rc = rwrt_ray_init(h, nsource, (const double *)(arena + o_slon), (const double *)(arena + o_slat), dmem, nzwn,
-                           (const double *)(arena + o_zwn), freq, nt, (double *)(arena + o_out), s);
-        if (rc) goto done;
-        rc = rwrt_ray_run_rk45(h, nsource, dmem, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags,
-                               (double *)(arena + o_out), (int64_t *)(arena + o_acc), nullptr, (int8_t *)(arena + o_st),
-                               (int64_t *)(arena + o_tot), s);
-        if (rc) goto done;
+    if (nsource > 0) {
+        CUX(cudaMemcpyAsync(arena + o_slon, src_lon, (size_t)nsource * 8, cudaMemcpyHostToDevice, s));
+        CUX(cudaMemcpyAsync(arena + o_slat, src_lat, (size_t)nsource * 8, cudaMemcpyHostToDevice, s));
+        if (src_member) CUX(cudaMemcpyAsync(arena + o_mem, src_member, (size_t)nsource * 4, cudaMemcpyHostToDevice, s));
     }
-    CUX(cudaMemcpyAsync(out7_host, arena + o_out, nout * 8, cudaMemcpyDeviceToHost, s));
-    if (accepted_host) CUX(cudaMemcpyAsync(accepted_host, arena + o_acc, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
-    if (status_host) CUX(cudaMemcpyAsync(status_host, arena + o_st, (size_t)N, cudaMemcpyDeviceToHost, s));
-    if (total_accepted_host) CUX(cudaMemcpyAsync(total_accepted_host, arena + o_tot, 8, cudaMemcpyDeviceToHost, s));
+    if (nzwn > 0) CUX(cudaMemcpyAsync(arena + o_zwn, zwn, (size_t)nzwn * 8, cudaMemcpyHostToDevice, s));
+    CUX(cudaMemsetAsync(arena + o_tot, 0, (size_t)(nchunk + 1) * 8, s));
+    rc = rwrt_bs_ready(h, (const float *)(arena + o_u), (const float *)(arena + o_v), (const double *)(arena + o_lon),
+                       (const double *)(arena + o_lat), (coslat && sinlat) ? (const double *)(arena + o_cl) : nullptr,
+                       (coslat && sinlat) ? (const double *)(arena + o_sl) : nullptr, nullptr, nullptr, s);
+    if (rc) goto done;
+    for (int c = 0; c < nchunk; ++c) {
+        const int b = c & 1;
+        const int s0 = c * chunk, ns = (s0 + chunk <= nsource) ? chunk : nsource - s0;
+        const long long N = 3LL * ns * nzwn;
+        const int32_t *dmem = src_member ? (const int32_t *)(arena + o_mem) + s0 : nullptr;
+        double *dout = (double *)(arena + o_out[b]);
+        if (c >= 2) CUX(cudaStreamWaitEvent(s, ev_copied[b], 0));  // the buffer's previous tenant has left
+        rc = rwrt_ray_init(h, ns, (const double *)(arena + o_slon) + s0, (const double *)(arena + o_slat) + s0, dmem,
+                           nzwn, (const double *)(arena + o_zwn), freq, nt, dout, s);
+        if (rc) goto done;
+        rc = rwrt_ray_run_rk45(h, ns, dmem, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, dout,
+                               (int64_t *)(arena + o_acc[b]), nullptr, (int8_t *)(arena + o_st[b]),
+                               (int64_t *)(arena + o_tot) + c, s);
+        if (rc) goto done;
+        CUX(cudaEventRecord(ev_done[b], s));
+        CUX(cudaStreamWaitEvent(cs, ev_done[b], 0));
+        if (N > 0) {
+            // device chunk (7*nt*3 rows of ns*nzwn doubles) -> host rows of nsource*nzwn doubles, column offset s0*nzwn
+            CUX(cudaMemcpy2DAsync(out7_host + (size_t)s0 * nzwn, (size_t)nsource * row_bytes_per_source, dout,
+                                  (size_t)ns * row_bytes_per_source, (size_t)ns * row_bytes_per_source, (size_t)7 * nt * 3,
+                                  cudaMemcpyDeviceToHost, cs));
+            if (accepted_host)
+                CUX(cudaMemcpy2DAsync(accepted_host + (size_t)s0 * nzwn, (size_t)nsource * nzwn * 8, arena + o_acc[b],
+                                      (size_t)ns * nzwn * 8, (size_t)ns * nzwn * 8, 3, cudaMemcpyDeviceToHost, cs));
+            if (status_host)
+                CUX(cudaMemcpy2DAsync(status_host + (size_t)s0 * nzwn, (size_t)nsource * nzwn, arena + o_st[b],
+                                      (size_t)ns * nzwn, (size_t)ns * nzwn, 3, cudaMemcpyDeviceToHost, cs));
+        }
+        CUX(cudaEventRecord(ev_copied[b], cs));
+    }
+    CUX(cudaMemcpyAsync(totals_host, arena + o_tot, (size_t)(nchunk + 1) * 8, cudaMemcpyDeviceToHost, s));
     CUX(cudaStreamSynchronize(s));
+    CUX(cudaStreamSynchronize(cs));
+    if (total_accepted_host) {
+        int64_t t = 0;
+        for (int c = 0; c < nchunk; ++c) t += totals_host[c];
+        *total_accepted_host = t;
+    }
 done:
+    if (cs) {
+        cudaStreamSynchronize(cs);
+        cudaStreamDestroy(cs);
+    }
+    for (int b = 0; b < 2; ++b) {
+        if (ev_done[b]) cudaEventDestroy(ev_done[b]);
+        if (ev_copied[b]) cudaEventDestroy(ev_copied[b]);
+    }
+    if (totals_host) cudaFreeHost(totals_host);
     cudaFree(arena);
     return rc;
 #undef CUX

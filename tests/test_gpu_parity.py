@@ -167,7 +167,7 @@ def test_vs_oracle_medium(strict):
     w = make_wr(u, v, zwn, slon, slat, 10.0)
     w.ray_run(mode="numpy", root_method="numpy", inte_method="rk45", strict=strict)
     got = {n: getattr(w, n) for n in parity.NAMES}
-    st = parity.compare(got, w.accepted, ref, acc, ng, "medium")
+    st = parity.compare(got, w.accepted, ref, acc, ng, "medium", max_outliers=int(ng.sum()) // 2000)
     print(st)
     assert st["nongrazing"] > 0.7 * st["live"]
     # whole-batch sanity: total accepted steps within 0.5 % of the oracle's even counting grazing rays
@@ -195,10 +195,12 @@ def test_batch_composition_independence():
         assert np.array_equal(first[n], getattr(w, n), equal_nan=True), n
 
 
-def test_c_abi_host_entry_equals_facade():
-    """rwrt_real2d_host (host pointers, H2D/D2H inside) returns what the facade returns."""
+def test_c_abi_host_entry_equals_facade(monkeypatch):
+    """rwrt_real2d_host (host pointers, H2D/D2H inside; sources processed in overlapped chunks) returns
+    what the facade returns -- with one chunk and with the chunking forced down to ~1 MB pieces."""
     u, v = synthetic.clim(144, 73)
-    sl, sa = synthetic.random_sources(50, 3)
+    ns = 120
+    sl, sa = synthetic.random_sources(ns, 3)
     slon, slat = np.radians(sl), np.radians(sa)
     zwn = np.array([1.0, 2.0, 4.0])
     days = 5.0
@@ -206,22 +208,26 @@ def test_c_abi_host_entry_equals_facade():
     w.ray_run(mode="numpy", inte_method="rk45")
     lon, lat = synthetic.grid_coords(144, 73)
     L = lib.load()
-    h = lib.vp()
-    lib.check(L.rwrt_create(0, 144, 73, 1, 1, C.byref(h)))
     nt = w.nt
-    out = np.empty((7, nt, 3, 50, 3))
-    acc = np.empty(3 * 50 * 3, dtype=np.int64)
-    status = np.empty(3 * 50 * 3, dtype=np.int8)
-    total = np.zeros(1, dtype=np.int64)
     cl, sn = np.cos(lat), np.sin(lat)
-    lib.check(L.rwrt_real2d_host(h, lib.ptr(u), lib.ptr(v), lib.ptr(lon), lib.ptr(lat), lib.ptr(cl), lib.ptr(sn), 50,
-                                 lib.ptr(slon), lib.ptr(slat), None, 3, lib.ptr(zwn), 0.0, nt, 7200.0, days * 86400.0,
-                                 1e-6, 1e-6, 1e-3, 0.1, lib.MODE_FAST, lib.ptr(out), lib.ptr(acc), lib.ptr(status),
-                                 lib.ptr(total), None), "rwrt_real2d_host")
-    for k, n in enumerate(parity.NAMES):
-        assert np.array_equal(out[k], getattr(w, n), equal_nan=True), n
-    assert np.array_equal(acc.reshape(3, 50, 3), w.accepted) and int(total[0]) == w.total_accepted
-    L.rwrt_destroy(h)
+    for chunk_mb in (None, "1"):
+        if chunk_mb:
+            monkeypatch.setenv("RWRT_HOST_CHUNK_MB", chunk_mb)      # 120 sources x 30.7 KB -> 4 chunks
+        h = lib.vp()
+        lib.check(L.rwrt_create(0, 144, 73, 1, 1, C.byref(h)))
+        out = np.full((7, nt, 3, ns, 3), -7.0)
+        acc = np.full(3 * ns * 3, -1, dtype=np.int64)
+        status = np.full(3 * ns * 3, -1, dtype=np.int8)
+        total = np.zeros(1, dtype=np.int64)
+        lib.check(L.rwrt_real2d_host(h, lib.ptr(u), lib.ptr(v), lib.ptr(lon), lib.ptr(lat), lib.ptr(cl), lib.ptr(sn), ns,
+                                     lib.ptr(slon), lib.ptr(slat), None, 3, lib.ptr(zwn), 0.0, nt, 7200.0,
+                                     days * 86400.0, 1e-6, 1e-6, 1e-3, 0.1, lib.MODE_FAST, lib.ptr(out), lib.ptr(acc),
+                                     lib.ptr(status), lib.ptr(total), None), "rwrt_real2d_host")
+        for k, n in enumerate(parity.NAMES):
+            assert np.array_equal(out[k], getattr(w, n), equal_nan=True), (chunk_mb, n)
+        assert np.array_equal(acc.reshape(3, ns, 3), w.accepted) and int(total[0]) == w.total_accepted
+        assert np.array_equal(status.reshape(3, ns, 3), w.status)
+        L.rwrt_destroy(h)
 
 
 def test_empty_and_error_paths():
