@@ -406,10 +406,14 @@ int rwrt_ray_init(rwrt_handle h, int nsource, const double *src_lon, const doubl
     return RWRT_OK;
 }
 
-int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
-                      double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
-                      double *out7, int64_t *accepted, int64_t *attempts, int8_t *status, int64_t *total_accepted,
-                      void *stream)
+// After each time window's kernel has been queued on `s`, hook(ctx, it_begin, it_end, s) may queue
+// follow-up work (the host entry copies the finished rows to the host on another stream).
+typedef int (*window_hook)(void *ctx, int it_begin, int it_end, cudaStream_t s);
+
+static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
+                    double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
+                    double *out7, int64_t *accepted, int64_t *attempts, int8_t *status, int64_t *total_accepted,
+                    void *stream, int nwin, window_hook hook, void *hook_ctx)
 {
     if (!h || nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45: bad sizes");
     if (!(tstep > 0)) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45: tstep must be positive");
@@ -443,7 +447,7 @@ int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int
     unsigned long long nlive = 0;
     CU(cudaMemcpyAsync(&nlive, ctr + 2, sizeof nlive, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));  // the one host sync of this call: grid sizes depend on nlive
-    if (nlive && h->state.reserve((size_t)nlive * 12 * sizeof(double)))
+    if (nlive && h->state.reserve((size_t)nlive * RWRT_STATE * sizeof(double)))
         return fail(RWRT_ERR_NOMEM, "ray state allocation failed (%llu rays)", nlive);
 
     // 2. parameters (rkf45.py:21-26 validate_tol; rkf45.py:362 Global_Minstep; wr.py:170 cut_off)
@@ -488,18 +492,47 @@ int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int
     CU(cudaEventRecord(h->ev0, s));
     CU(cudaEventRecord(h->ev_fork, s));            // fork: the side stream starts after everything queued so far
     CU(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-    if (strict) launch_rk45_strict(p, prepare_blocks, fill_blocks, integrate_blocks, s, h->aux);
-    else launch_rk45_fast(p, prepare_blocks, fill_blocks, integrate_blocks, s, h->aux);
+    p.it_begin = 1;
+    p.it_end = nt;
+    if (strict) launch_rk45_setup_strict(p, prepare_blocks, fill_blocks, s, h->aux);
+    else launch_rk45_setup_fast(p, prepare_blocks, fill_blocks, s, h->aux);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(h->ev_join, h->aux));       // join: the caller's stream continues after both are done
-    CU(cudaStreamWaitEvent(s, h->ev_join, 0));
+    CU(cudaEventRecord(h->ev_join, h->aux));
+    if (!coop || nwin < 1) nwin = 1;               // only the cooperative kernel can park rays at a window end
+    if (nwin > nt - 1) nwin = nt - 1;
+    int launches = 0;
+    for (int w = 0; w < nwin; ++w) {
+        p.it_begin = 1 + (int)((long long)(nt - 1) * w / nwin);
+        p.it_end = 1 + (int)((long long)(nt - 1) * (w + 1) / nwin);
+        if (w > 0) CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));  // rewind the work queue
+        if (strict) launch_rk45_window_strict(p, integrate_blocks, s);
+        else launch_rk45_window_fast(p, integrate_blocks, s);
+        CU(cudaGetLastError());
+        ++launches;
+        if (w == 0) CU(cudaStreamWaitEvent(s, h->ev_join, 0));  // join: rows of NaN-root slots are complete too
+        if (hook) {
+            int rc = hook(hook_ctx, p.it_begin, p.it_end, s);
+            if (rc) return rc;
+        }
+    }
     CU(cudaEventRecord(h->ev1, s));
     h->timed = true;
-    h->last_launches = 3 + (nlive ? 3 : 1);  // compaction (3) + fill + prepare + integrate
+    h->last_launches = 3 + 1 + (nlive ? 1 + launches : 0);  // compaction (3) + fill + prepare + integrate windows
     h->last_nlive = (double)nlive;
     if (total_accepted)
         CU(cudaMemcpyAsync(total_accepted, ctr + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
     return RWRT_OK;
+}
+
+int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
+                      double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
+                      double *out7, int64_t *accepted, int64_t *attempts, int8_t *status, int64_t *total_accepted,
+                      void *stream)
+{
+    int nwin = 1;
+    if (const char *e = getenv("RWRT_WINDOWS")) nwin = atoi(e);  // tuning / testing: split the run into time windows
+    return run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7,
+                    accepted, attempts, status, total_accepted, stream, nwin, nullptr, nullptr);
 }
 
 int rwrt_last_run_stats(rwrt_handle h, double *stats3)
@@ -539,6 +572,38 @@ int rwrt_grid_accumulate(rwrt_handle h, int64_t nslot, int nt, const double *out
     return RWRT_OK;
 }
 
+namespace {
+struct HostCopyCtx {
+    cudaStream_t copy_stream;
+    cudaEvent_t ev[2];
+    int n_ev;
+    const double *dev;
+    double *host;
+    long long N;
+    int nt;
+    bool first;
+};
+
+// window hook of rwrt_real2d_host: rows [it_begin, it_end) of the seven planes are final once this window's
+// kernel has finished -> ship them on the copy stream (7 contiguous copies) while the next window integrates.
+int host_copy_hook(void *vctx, int it_begin, int it_end, cudaStream_t s)
+{
+    HostCopyCtx *c = (HostCopyCtx *)vctx;
+    cudaEvent_t e = c->ev[c->n_ev & 1];
+    ++c->n_ev;
+    CU(cudaEventRecord(e, s));
+    CU(cudaStreamWaitEvent(c->copy_stream, e, 0));
+    int r0 = c->first ? 0 : it_begin;  // the t = 0 row travels with the first window
+    c->first = false;
+    for (int pl = 0; pl < 7; ++pl) {
+        size_t off = ((size_t)pl * c->nt + r0) * (size_t)c->N;
+        CU(cudaMemcpyAsync(c->host + off, c->dev + off, (size_t)(it_end - r0) * c->N * sizeof(double),
+                           cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    return RWRT_OK;
+}
+}  // namespace
+
 int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
                      const double *coslat, const double *sinlat, int nsource, const double *src_lon,
                      const double *src_lat, const int32_t *src_member, int nzwn, const double *zwn, double freq, int nt,
@@ -552,39 +617,34 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaSetDevice(h->device));
     const size_t ng = (size_t)h->nmember * h->nlon * h->nlat;
-    // The sources are processed in chunks: while chunk c integrates, the trajectories of chunk c-1 travel to
-    // the host on the copy stream (strided 2-D copies into the reference layout (7, nt, 3, nsource, nzwn)).
-    // Chunking is exact: a ray's result does not depend on its batch.
-    const size_t row_bytes_per_source = (size_t)nzwn * sizeof(double);
-    const size_t bytes_per_source = (size_t)7 * nt * 3 * row_bytes_per_source;
-    size_t target = (size_t)4 << 30;  // ~4 GB of trajectories per chunk
-    if (const char *e = getenv("RWRT_HOST_CHUNK_MB")) target = (size_t)strtoll(e, nullptr, 10) << 20;
-    int chunk = nsource;
-    if (bytes_per_source > 0 && (size_t)nsource * bytes_per_source > target + target / 2) {
-        chunk = (int)(target / bytes_per_source);
-        if (chunk < 1) chunk = 1;
-    }
-    const int nchunk = nsource > 0 ? (nsource + chunk - 1) / chunk : 0;
-    const long long Nc = 3LL * chunk * nzwn;
-    const size_t out_chunk = (size_t)7 * nt * Nc;
-    // one device arena for every input and the two chunk buffers
+    const long long N = 3LL * nsource * nzwn;
+    const size_t nout = (size_t)7 * nt * N;
+    // The integration runs in time windows; the rows of a finished window travel to the host on a second
+    // stream (contiguous copies in the reference layout) while the next window integrates.
+    int nwin = (int)((nout * sizeof(double)) >> 30);  // ~1 GB of trajectories per window (measured on C2: 1 / 4 / 10 / 24
+                                                      // windows -> 683 / 631 / 548 / 492 ms per pass on the same box)
+    if (const char *e = getenv("RWRT_HOST_WINDOWS")) nwin = atoi(e);
+    if (nwin < 1) nwin = 1;
+    if (nwin > 64) nwin = 64;
+    // one device arena for every input and output of the call
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     size_t o_u = carve(ng * 4), o_v = carve(ng * 4), o_lon = carve((size_t)h->nlon * 8), o_lat = carve((size_t)h->nlat * 8);
     size_t o_cl = carve((size_t)h->nlat * 8), o_sl = carve((size_t)h->nlat * 8);
     size_t o_slon = carve((size_t)nsource * 8), o_slat = carve((size_t)nsource * 8), o_mem = carve((size_t)nsource * 4);
-    size_t o_zwn = carve((size_t)nzwn * 8), o_tot = carve((size_t)(nchunk + 1) * 8);
-    size_t o_acc[2], o_st[2], o_out[2];
-    for (int b = 0; b < 2; ++b) {
-        o_acc[b] = carve((size_t)Nc * 8);
-        o_st[b] = carve((size_t)Nc);
-        o_out[b] = carve(out_chunk * 8);
-    }
+    size_t o_zwn = carve((size_t)nzwn * 8), o_acc = carve((size_t)N * 8), o_st = carve((size_t)N), o_tot = carve(8);
+    size_t o_out = carve(nout * 8);
     char *arena = nullptr;
     CU(cudaMalloc((void **)&arena, off));
-    cudaStream_t cs = nullptr;
-    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-    int64_t *totals_host = nullptr;
+    HostCopyCtx ctx;
+    ctx.copy_stream = nullptr;
+    ctx.ev[0] = ctx.ev[1] = nullptr;
+    ctx.n_ev = 0;
+    ctx.dev = (const double *)(arena + o_out);
+    ctx.host = out7_host;
+    ctx.N = N;
+    ctx.nt = nt;
+    ctx.first = true;
     int rc = RWRT_OK;
 #define CUX(call)                                                                                       \
     do {                                                                                                \
@@ -594,12 +654,9 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
             goto done;                                                                                  \
         }                                                                                               \
     } while (0)
-    CUX(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) {
-        CUX(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
-        CUX(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
-    }
-    CUX(cudaMallocHost((void **)&totals_host, (size_t)(nchunk + 1) * 8));
+    CUX(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
+    CUX(cudaEventCreateWithFlags(&ctx.ev[0], cudaEventDisableTiming));
+    CUX(cudaEventCreateWithFlags(&ctx.ev[1], cudaEventDisableTiming));
     CUX(cudaMemcpyAsync(arena + o_u, u, ng * 4, cudaMemcpyHostToDevice, s));
     CUX(cudaMemcpyAsync(arena + o_v, v, ng * 4, cudaMemcpyHostToDevice, s));
     CUX(cudaMemcpyAsync(arena + o_lon, lon, (size_t)h->nlon * 8, cudaMemcpyHostToDevice, s));
@@ -614,59 +671,35 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
         if (src_member) CUX(cudaMemcpyAsync(arena + o_mem, src_member, (size_t)nsource * 4, cudaMemcpyHostToDevice, s));
     }
     if (nzwn > 0) CUX(cudaMemcpyAsync(arena + o_zwn, zwn, (size_t)nzwn * 8, cudaMemcpyHostToDevice, s));
-    CUX(cudaMemsetAsync(arena + o_tot, 0, (size_t)(nchunk + 1) * 8, s));
-    rc = rwrt_bs_ready(h, (const float *)(arena + o_u), (const float *)(arena + o_v), (const double *)(arena + o_lon),
-                       (const double *)(arena + o_lat), (coslat && sinlat) ? (const double *)(arena + o_cl) : nullptr,
-                       (coslat && sinlat) ? (const double *)(arena + o_sl) : nullptr, nullptr, nullptr, s);
-    if (rc) goto done;
-    for (int c = 0; c < nchunk; ++c) {
-        const int b = c & 1;
-        const int s0 = c * chunk, ns = (s0 + chunk <= nsource) ? chunk : nsource - s0;
-        const long long N = 3LL * ns * nzwn;
-        const int32_t *dmem = src_member ? (const int32_t *)(arena + o_mem) + s0 : nullptr;
-        double *dout = (double *)(arena + o_out[b]);
-        if (c >= 2) CUX(cudaStreamWaitEvent(s, ev_copied[b], 0));  // the buffer's previous tenant has left
-        rc = rwrt_ray_init(h, ns, (const double *)(arena + o_slon) + s0, (const double *)(arena + o_slat) + s0, dmem,
-                           nzwn, (const double *)(arena + o_zwn), freq, nt, dout, s);
+    CUX(cudaMemsetAsync(arena + o_tot, 0, 8, s));
+    {
+        const int32_t *dmem = src_member ? (const int32_t *)(arena + o_mem) : nullptr;
+        rc = rwrt_bs_ready(h, (const float *)(arena + o_u), (const float *)(arena + o_v), (const double *)(arena + o_lon),
+                           (const double *)(arena + o_lat), (coslat && sinlat) ? (const double *)(arena + o_cl) : nullptr,
+                           (coslat && sinlat) ? (const double *)(arena + o_sl) : nullptr, nullptr, nullptr, s);
         if (rc) goto done;
-        rc = rwrt_ray_run_rk45(h, ns, dmem, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, dout,
-                               (int64_t *)(arena + o_acc[b]), nullptr, (int8_t *)(arena + o_st[b]),
-                               (int64_t *)(arena + o_tot) + c, s);
+        rc = rwrt_ray_init(h, nsource, (const double *)(arena + o_slon), (const double *)(arena + o_slat), dmem, nzwn,
+                           (const double *)(arena + o_zwn), freq, nt, (double *)(arena + o_out), s);
         if (rc) goto done;
-        CUX(cudaEventRecord(ev_done[b], s));
-        CUX(cudaStreamWaitEvent(cs, ev_done[b], 0));
-        if (N > 0) {
-            // device chunk (7*nt*3 rows of ns*nzwn doubles) -> host rows of nsource*nzwn doubles, column offset s0*nzwn
-            CUX(cudaMemcpy2DAsync(out7_host + (size_t)s0 * nzwn, (size_t)nsource * row_bytes_per_source, dout,
-                                  (size_t)ns * row_bytes_per_source, (size_t)ns * row_bytes_per_source, (size_t)7 * nt * 3,
-                                  cudaMemcpyDeviceToHost, cs));
-            if (accepted_host)
-                CUX(cudaMemcpy2DAsync(accepted_host + (size_t)s0 * nzwn, (size_t)nsource * nzwn * 8, arena + o_acc[b],
-                                      (size_t)ns * nzwn * 8, (size_t)ns * nzwn * 8, 3, cudaMemcpyDeviceToHost, cs));
-            if (status_host)
-                CUX(cudaMemcpy2DAsync(status_host + (size_t)s0 * nzwn, (size_t)nsource * nzwn, arena + o_st[b],
-                                      (size_t)ns * nzwn, (size_t)ns * nzwn, 3, cudaMemcpyDeviceToHost, cs));
-        }
-        CUX(cudaEventRecord(ev_copied[b], cs));
+        rc = run_rk45(h, nsource, dmem, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags,
+                      (double *)(arena + o_out), (int64_t *)(arena + o_acc), nullptr, (int8_t *)(arena + o_st),
+                      (int64_t *)(arena + o_tot), s, nwin, host_copy_hook, &ctx);
+        if (rc) goto done;
     }
-    CUX(cudaMemcpyAsync(totals_host, arena + o_tot, (size_t)(nchunk + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (ctx.first && nout > 0)  // nothing was integrated (no live ray / nt == 1): plain copy of what there is
+        CUX(cudaMemcpyAsync(out7_host, arena + o_out, nout * 8, cudaMemcpyDeviceToHost, s));
+    if (accepted_host && N > 0) CUX(cudaMemcpyAsync(accepted_host, arena + o_acc, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
+    if (status_host && N > 0) CUX(cudaMemcpyAsync(status_host, arena + o_st, (size_t)N, cudaMemcpyDeviceToHost, s));
+    if (total_accepted_host) CUX(cudaMemcpyAsync(total_accepted_host, arena + o_tot, 8, cudaMemcpyDeviceToHost, s));
     CUX(cudaStreamSynchronize(s));
-    CUX(cudaStreamSynchronize(cs));
-    if (total_accepted_host) {
-        int64_t t = 0;
-        for (int c = 0; c < nchunk; ++c) t += totals_host[c];
-        *total_accepted_host = t;
-    }
+    CUX(cudaStreamSynchronize(ctx.copy_stream));
 done:
-    if (cs) {
-        cudaStreamSynchronize(cs);
-        cudaStreamDestroy(cs);
+    if (ctx.copy_stream) {
+        cudaStreamSynchronize(ctx.copy_stream);
+        cudaStreamDestroy(ctx.copy_stream);
     }
-    for (int b = 0; b < 2; ++b) {
-        if (ev_done[b]) cudaEventDestroy(ev_done[b]);
-        if (ev_copied[b]) cudaEventDestroy(ev_copied[b]);
-    }
-    if (totals_host) cudaFreeHost(totals_host);
+    if (ctx.ev[0]) cudaEventDestroy(ctx.ev[0]);
+    if (ctx.ev[1]) cudaEventDestroy(ctx.ev[1]);
     cudaFree(arena);
     return rc;
 #undef CUX

@@ -108,11 +108,16 @@ __global__ void __launch_bounds__(128) rk45_prepare(RunParams p)
     const double *fb = member_base(p, slot);
     ray_rhs<RWRT_FAST>(p.g, fb, y, f);
     double h = initial_step(p.g, fb, y, f, p.rtol, p.atol);
-    double *st = p.state + (size_t)i * 12;
+    double *st = p.state + (size_t)i * RWRT_STATE;
 #pragma unroll
     for (int c = 0; c < 5; ++c) { st[c] = y[c]; st[5 + c] = f[c]; }
     st[10] = h;
-    st[11] = 0.0;
+    st[11] = cos(y[1]);   // cos(latitude of the previous output)
+    st[12] = 0.0;         // t
+    st[13] = y[0];        // previous output position
+    st[14] = y[1];
+    reinterpret_cast<int *>(st + 15)[0] = 0;  // accepted so far
+    reinterpret_cast<int *>(st + 15)[1] = 0;  // attempts so far; bit 31 set = ray finished
 }
 
 // NaN-root slots: rlon, rlat, rzwn keep their t=0 value at every output
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
             if (idle) {
                 unsigned long long mine = base + __popc(idle_mask & ((1u << lane_id) - 1));
                 if (mine < (unsigned long long)p.nlive) {
-                    const double *st = p.state + (size_t)mine * 12;
+                    const double *st = p.state + (size_t)mine * RWRT_STATE;
                     L.slot = p.live[mine];
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
@@ -425,6 +430,8 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
     const int q8 = lane_id & 7, grp = lane_id >> 3;
     double pcos = 1.0;                                                     // cos(latitude of the previous output)
     const double *prev_rec = nullptr;                                      // cell record currently staged for this lane
+    long long my_ray = -1;                                                 // index of this lane's ray in the state array
+    int acc0 = 0;                                                          // accepted steps when this launch picked the ray up
     const double shc = sin(0.5 * p.cut), sin2_half_cut = (p.cut >= PI) ? 2.0 : shc * shc;  // angle <= pi: never cut
     // own-record read offsets: logical 16-byte chunk q of ray r lives at r*384 + (q>>3)*128 + ((q&7)^(r&7))*16
     const unsigned char *my_rec = stage + lane_id * 384;
@@ -447,25 +454,30 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             if (idle) {
                 unsigned long long mine = base + __popc(idle_mask & ((1u << lane_id) - 1));
                 if (mine < (unsigned long long)p.nlive) {
-                    const double *st = p.state + (size_t)mine * 12;
-                    L.slot = p.live[mine];
+                    const double *st = p.state + (size_t)mine * RWRT_STATE;
+                    const int att0 = reinterpret_cast<const int *>(st + 15)[1];
+                    if (att0 >= 0) {  // not finished in an earlier time window
+                        my_ray = (long long)mine;
+                        L.slot = p.live[mine];
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        L.y[c] = st[c];
-                        k1[c] = st[5 + c];
+                        for (int c = 0; c < 5; ++c) {
+                            L.y[c] = st[c];
+                            k1[c] = st[5 + c];
+                        }
+                        L.h_abs = st[10];
+                        pcos = st[11];
+                        L.t = st[12];
+                        L.plon = st[13];
+                        L.plat = st[14];
+                        L.acc = reinterpret_cast<const int *>(st + 15)[0];
+                        acc0 = L.acc;
+                        L.att = att0;
+                        L.it = p.it_begin;
+                        L.rejected = false;
+                        L.fresh = true;
+                        fb = member_base(p, L.slot);
+                        fcb = p.g.fcell + (fb - p.g.fpk) / p.g.member_stride * p.g.cell_member_stride;
                     }
-                    L.h_abs = st[10];
-                    L.t = 0.0;
-                    L.plon = L.y[0];
-                    L.plat = L.y[1];
-                    pcos = cos(L.plat);
-                    L.acc = 0;
-                    L.att = 0;
-                    L.it = 1;
-                    L.rejected = false;
-                    L.fresh = true;
-                    fb = member_base(p, L.slot);
-                    fcb = p.g.fcell + (fb - p.g.fpk) / p.g.member_stride * p.g.cell_member_stride;
                 }
             }
         }
@@ -632,11 +644,29 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             pcos = masked ? cos(L.y[1]) : cos_new;
             ++L.it;
         }
-        if (dead || L.it >= p.nt) {  // ray finished: publish counters, free the lane
-            if (p.accepted) p.accepted[L.slot] = L.acc;
-            if (p.attempts) p.attempts[L.slot] = L.att;
-            if (p.status) p.status[L.slot] = (signed char)code;
-            my_total += L.acc;
+        const bool finished = dead || L.it >= p.nt;
+        if (finished || L.it >= p.it_end) {  // ray finished, or parked at the end of this time window
+            double *st = p.state + (size_t)my_ray * RWRT_STATE;
+            if (finished) {
+                if (p.accepted) p.accepted[L.slot] = L.acc;
+                if (p.attempts) p.attempts[L.slot] = L.att;
+                if (p.status) p.status[L.slot] = (signed char)code;
+                reinterpret_cast<int *>(st + 15)[1] = L.att | (int)0x80000000;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    st[c] = L.y[c];
+                    st[5 + c] = k1[c];
+                }
+                st[10] = L.h_abs;
+                st[11] = pcos;
+                st[12] = L.t;
+                st[13] = L.plon;
+                st[14] = L.plat;
+                reinterpret_cast<int *>(st + 15)[0] = L.acc;
+                reinterpret_cast<int *>(st + 15)[1] = L.att;
+            }
+            my_total += L.acc - acc0;
             L.slot = -1;
 #pragma unroll
             for (int c = 0; c < 5; ++c) {

@@ -4,6 +4,8 @@
 
 namespace rwrt {
 
+constexpr int RWRT_STATE = 16;  // doubles per live ray in the state array (128 B)
+
 struct RunParams {
     Grid g;
     const int32_t *src_member;  // (nsource) or nullptr
@@ -13,7 +15,8 @@ struct RunParams {
     double *out;                // 7 planes, each (nt, N)
     const int32_t *live;        // compacted list of live slots
     long long nlive;
-    double *state;              // (nlive, 12): y[5], f[5], h_abs, pad
+    double *state;              // (nlive, RWRT_STATE): y[5], f[5], h_abs, cos(prev lat), t, prev lon, prev lat, counters
+    int it_begin, it_end;       // this launch produces output rows [it_begin, it_end) (time window)
     long long *accepted;        // (N) or nullptr
     long long *attempts;        // (N) or nullptr
     signed char *status;        // (N) or nullptr

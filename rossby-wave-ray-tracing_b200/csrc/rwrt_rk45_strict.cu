@@ -5,21 +5,23 @@
 #include "rwrt_internal.h"
 
 namespace rwrt {
-void launch_rk45_strict(const RunParams &p, int prepare_blocks, int fill_blocks, int integrate_blocks, cudaStream_t s,
-                      cudaStream_t aux)
+void launch_rk45_setup_strict(const RunParams &p, int prepare_blocks, int fill_blocks, cudaStream_t s, cudaStream_t aux)
 {
-    if (p.nlive > 0) {
-        strict::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
-        if (p.g.fcell)
-            strict::rk45_integrate_coop<<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
-        else
-            strict::rk45_integrate<<<integrate_blocks, strict::RK_THREADS, strict::RK_SMEM_BYTES, s>>>(p);
-    }
-    // The constant rows of NaN-root slots touch no slot the integrator writes.  They go to the (low-priority)
-    // side stream AFTER the persistent integrator was queued, so their blocks fill the SMs that the
-    // integrator's tail leaves idle instead of delaying its start.
+    if (p.nlive > 0) strict::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
+    // The constant rows of NaN-root slots touch no slot the integrator writes: low-priority side stream.
     if (p.N > 0 && p.nt > 1)
         strict::fill_static_slots<<<dim3(fill_blocks, p.nt - 1 < 8 ? p.nt - 1 : 8), 256, 0, aux>>>(p);
+}
+
+// One time window [p.it_begin, p.it_end) of output rows for every live ray (the point-major kernel has no
+// windows: it is launched once with the whole range).
+void launch_rk45_window_strict(const RunParams &p, int integrate_blocks, cudaStream_t s)
+{
+    if (p.nlive <= 0) return;
+    if (p.g.fcell)
+        strict::rk45_integrate_coop<<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
+    else
+        strict::rk45_integrate<<<integrate_blocks, strict::RK_THREADS, strict::RK_SMEM_BYTES, s>>>(p);
 }
 int occupancy_rk45_strict(bool coop)
 {

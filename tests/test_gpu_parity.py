@@ -190,14 +190,25 @@ def test_batch_composition_independence():
     assert np.array_equal(w.accepted[:, 100:180, :], w2.accepted)
     # idempotence: running again reproduces the same bits (no order-dependent state in the engine)
     first = {n: getattr(w, n).copy() for n in parity.NAMES}
+    first_acc = w.accepted.copy()
     w.ray_run(mode="numpy", inte_method="rk45")
     for n in parity.NAMES:
         assert np.array_equal(first[n], getattr(w, n), equal_nan=True), n
+    # time windows (rays parked at a window end, state saved and restored) are exact as well
+    import os
+    os.environ["RWRT_WINDOWS"] = "7"
+    try:
+        w.ray_run(mode="numpy", inte_method="rk45")
+    finally:
+        del os.environ["RWRT_WINDOWS"]
+    for n in parity.NAMES:
+        assert np.array_equal(first[n], getattr(w, n), equal_nan=True), ("windows", n)
+    assert np.array_equal(first_acc, w.accepted)
 
 
 def test_c_abi_host_entry_equals_facade(monkeypatch):
-    """rwrt_real2d_host (host pointers, H2D/D2H inside; sources processed in overlapped chunks) returns
-    what the facade returns -- with one chunk and with the chunking forced down to ~1 MB pieces."""
+    """rwrt_real2d_host (host pointers, H2D/D2H inside; integration in time windows whose finished rows are
+    copied back while the next window runs) returns what the facade returns -- with 1 and with 4 windows."""
     u, v = synthetic.clim(144, 73)
     ns = 120
     sl, sa = synthetic.random_sources(ns, 3)
@@ -210,9 +221,8 @@ def test_c_abi_host_entry_equals_facade(monkeypatch):
     L = lib.load()
     nt = w.nt
     cl, sn = np.cos(lat), np.sin(lat)
-    for chunk_mb in (None, "1"):
-        if chunk_mb:
-            monkeypatch.setenv("RWRT_HOST_CHUNK_MB", chunk_mb)      # 120 sources x 30.7 KB -> 4 chunks
+    for chunk_mb in ("1", "4"):
+        monkeypatch.setenv("RWRT_HOST_WINDOWS", chunk_mb)
         h = lib.vp()
         lib.check(L.rwrt_create(0, 144, 73, 1, 1, C.byref(h)))
         out = np.full((7, nt, 3, ns, 3), -7.0)
