@@ -121,6 +121,17 @@ int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int
                       int64_t *total_accepted, void *stream);
 
 /*
+ * Same as rwrt_ray_run_rk45, and additionally delivers the seven result planes to HOST memory
+ * out7_host (7, nt, 3, nsource, nzwn) -- pinned memory (rwrt_host_alloc) makes it asynchronous: the
+ * integration runs in time windows and the finished rows of a window are copied while the next one
+ * integrates.  out7 is the device buffer (row 0 = initial state, as above).  Synchronises before returning.
+ */
+int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
+                          double ttotal, double rtol, double atol, double min_step_factor, double cut_off,
+                          uint32_t flags, double *out7, int64_t *accepted, int64_t *attempts, int8_t *status,
+                          int64_t *total_accepted, double *out7_host, void *stream);
+
+/*
  * Ray-density / wave-ray-flux gridding of trajectories (manual section 4; no reference code --
  * parity unpinned, defined by oracle/gridding.py).  The domain is three longitude circles
  * [-360, 720) deg x [-90, 90] deg with cells of (dlon_deg, dlat_deg).  For every output time it >= 1

@@ -604,6 +604,46 @@ int host_copy_hook(void *vctx, int it_begin, int it_end, cudaStream_t s)
 }
 }  // namespace
 
+int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
+                          double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
+                          double *out7, int64_t *accepted, int64_t *attempts, int8_t *status, int64_t *total_accepted,
+                          double *out7_host, void *stream)
+{
+    if (!h || !out7_host) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45_d2h: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->device));
+    const long long N = 3LL * nsource * nzwn;
+    const size_t nout = (size_t)7 * nt * N;
+    int nwin = (int)((nout * sizeof(double)) >> 30);
+    if (const char *e = getenv("RWRT_HOST_WINDOWS")) nwin = atoi(e);
+    if (nwin < 1) nwin = 1;
+    if (nwin > 64) nwin = 64;
+    HostCopyCtx ctx;
+    ctx.copy_stream = nullptr;
+    ctx.ev[0] = ctx.ev[1] = nullptr;
+    ctx.n_ev = 0;
+    ctx.dev = out7;
+    ctx.host = out7_host;
+    ctx.N = N;
+    ctx.nt = nt;
+    ctx.first = true;
+    CU(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx.ev[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx.ev[1], cudaEventDisableTiming));
+    int rc = run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7,
+                      accepted, attempts, status, total_accepted, stream, nwin, host_copy_hook, &ctx);
+    if (rc == RWRT_OK && ctx.first && nout > 0 && out7) {
+        cudaError_t e = cudaMemcpyAsync(out7_host, out7, nout * 8, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = fail(RWRT_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamSynchronize(ctx.copy_stream);
+    cudaStreamDestroy(ctx.copy_stream);
+    cudaEventDestroy(ctx.ev[0]);
+    cudaEventDestroy(ctx.ev[1]);
+    return rc;
+}
+
 int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
                      const double *coslat, const double *sinlat, int nsource, const double *src_lon,
                      const double *src_lat, const int32_t *src_member, int nzwn, const double *zwn, double freq, int nt,

@@ -145,8 +145,9 @@ class WR:
                                                  float(self.freq[0]), self.nt, _lib.ptr(self.d_out),
                                                  _lib.stream_ptr()), "rwrt_ray_init")
 
-    def core_ray_run(self, mode="numpy_rk45", strict=False):
-        """wr.py:767-887 (mode 'numpy_rk45')."""
+    def core_ray_run(self, mode="numpy_rk45", strict=False, to_host=False):
+        """wr.py:767-887 (mode 'numpy_rk45').  to_host: also deliver the seven planes to the pinned NumPy
+        arrays, overlapped with the integration (time windows, `rwrt_ray_run_rk45_d2h`)."""
         if mode != "numpy_rk45":
             raise NotImplementedError("only the RK45 path (mode='numpy', inte_method='rk45') exists on the GPU engine")
         import torch
@@ -156,12 +157,16 @@ class WR:
         self._d_status = torch.zeros(N, dtype=torch.int8, device=dev)
         self._d_total = torch.zeros(1, dtype=torch.int64, device=dev)
         flags = _lib.MODE_STRICT if strict else _lib.MODE_FAST
-        with torch.cuda.device(self.bs.device):
-            _lib.check(_lib.load().rwrt_ray_run_rk45(
-                self.bs._h, self.nsource, None, self.nzwn, self.nt, float(self.tstep[0]), float(self.ttotal),
+        args = (self.bs._h, self.nsource, None, self.nzwn, self.nt, float(self.tstep[0]), float(self.ttotal),
                 float(self.rtol), float(self.atol), float(self.MinStepFactor), float(self.cut_off_factor), flags,
-                _lib.ptr(self.d_out), _lib.ptr(self._d_acc), None, _lib.ptr(self._d_status), _lib.ptr(self._d_total),
-                _lib.stream_ptr()), "rwrt_ray_run_rk45")
+                _lib.ptr(self.d_out), _lib.ptr(self._d_acc), None, _lib.ptr(self._d_status), _lib.ptr(self._d_total))
+        with torch.cuda.device(self.bs.device):
+            if to_host and hasattr(self, "_host_t") and N > 0:
+                _lib.check(_lib.load().rwrt_ray_run_rk45_d2h(*args, _lib.ptr(self._host_t), _lib.stream_ptr()),
+                           "rwrt_ray_run_rk45_d2h")
+                return True
+            _lib.check(_lib.load().rwrt_ray_run_rk45(*args, _lib.stream_ptr()), "rwrt_ray_run_rk45")
+        return False
 
     def ray_run(self, mode="original", inte_method="", root_method="Fortran", debug=False, debug_file=None,
                 to_host=True, strict=False):
@@ -173,14 +178,16 @@ class WR:
         if debug:
             raise NotImplementedError("debug / debug_file (Fortran parity hooks, wr.py:901-906) are not supported")
         self.ray_initial(mode="numpy", root_method=root_method)
-        self.core_ray_run("numpy_rk45", strict=strict)
+        if to_host:
+            self._host_planes()          # the (pinned) result arrays exist before the run
+        delivered = self.core_ray_run("numpy_rk45", strict=strict, to_host=to_host)
         import torch
         torch.cuda.synchronize(self.bs.device)
         shp = (3, self.nsource, self.nzwn)
         self.total_accepted = int(self._d_total.item())
         self.accepted = self._d_acc.cpu().numpy().reshape(shp)
         self.status = self._d_status.cpu().numpy().reshape(shp)
-        if to_host:
+        if to_host and not delivered:
             self.to_host()
 
     def to_host(self):
