@@ -121,6 +121,13 @@ int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int
                       int64_t *total_accepted, void *stream);
 
 /*
+ * WR.core_ray_run_numpy (wr.py:702-765): the fixed-step RK4 path (inte_method = '', main_wr.py's default)
+ * with rk4_step_numpy's freeze-on-failure semantics (wr.py:583-622).  Same out7 convention as above.
+ */
+int rwrt_ray_run_rk4(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
+                     double cut_off, uint32_t flags, double *out7, int8_t *status, void *stream);
+
+/*
  * Same as rwrt_ray_run_rk45, and additionally delivers the seven result planes to HOST memory
  * out7_host (7, nt, 3, nsource, nzwn) -- pinned memory (rwrt_host_alloc) makes it asynchronous: the
  * integration runs in time windows and the finished rows of a window are copied while the next one

@@ -52,10 +52,11 @@ def nongrazing_mask(ref, per):
     return ok
 
 
-def trajectory_fixture(name, background, bg_kwargs, zwn, src_lon, src_lat, days, freq=0.0, tstep_h=2.0):
+def trajectory_fixture(name, background, bg_kwargs, zwn, src_lon, src_lat, days, freq=0.0, tstep_h=2.0, rk4=False):
     u, v = getattr(synthetic, background)(**bg_kwargs)
+    run = refshim.run_rk4 if rk4 else refshim.run_rk45
     w = refshim.make_wr(u, v, zwn, src_lon, src_lat, tstep_h=tstep_h, ttotal_d=days, freq=freq)
-    ref = refshim.run_rk45(w)
+    ref = run(w)
     # four perturbed runs of the reference: every source longitude / latitude moved by +-1 ulp (radians)
     ng = np.ones(ref["accepted"].shape, dtype=bool)
     for dlon_dir, dlat_dir in ((np.inf, None), (-np.inf, None), (None, np.inf), (None, -np.inf)):
@@ -64,7 +65,7 @@ def trajectory_fixture(name, background, bg_kwargs, zwn, src_lon, src_lat, days,
             w2.source_lon = np.nextafter(w.source_lon, dlon_dir)
         if dlat_dir is not None:
             w2.source_lat = np.nextafter(w.source_lat, dlat_dir)
-        ng &= nongrazing_mask(ref, refshim.run_rk45(w2))
+        ng &= nongrazing_mask(ref, run(w2))
     live = ~np.isnan(ref["rmwn"][0])
     print(f"{name}: slots {live.size}, live {live.sum()}, non-grazing live {np.sum(ng & live)}, "
           f"accepted {ref['accepted'].sum()}")
@@ -215,6 +216,10 @@ def main():
     # 1 degree grid, short
     sl, sa = synthetic.random_sources(10, 23)
     trajectory_fixture("clim_g2", "clim", dict(nlon=360, nlat=181), [2.0, 4.0, 6.0], sl, sa, 6.0)
+    # the fixed-step RK4 path (inte_method='', main_wr.py's default): wr.py:702-765
+    trajectory_fixture("rk4_jet", "jet_z", {}, [1.0, 2.0, 3.0], [120.0, 60.0], [30.0, 20.0], 20.0, rk4=True)
+    sl, sa = synthetic.random_sources(14, 31)
+    trajectory_fixture("rk4_clim_g1", "clim", dict(nlon=144, nlat=73), [1.0, 2.0, 4.0], sl, sa, 10.0, rk4=True)
 
 
 if __name__ == "__main__":

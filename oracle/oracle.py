@@ -38,6 +38,8 @@ def lib():
         L.orc_ray_run_rk45.restype = C.c_int
         L.orc_ray_run_rk45.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_int64, C.c_int, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_double, C.c_double, _dp, _ip, _ip]
+        L.orc_ray_run_rk4.restype = C.c_int
+        L.orc_ray_run_rk4.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_int64, C.c_int, C.c_double, C.c_double, _dp]
         L.orc_kat.restype = C.c_int64
         L.orc_kat.argtypes = [C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
         L.orc_ray_init.restype = C.c_int
@@ -116,6 +118,17 @@ def ray_run_rk45(fields, lon, lat, out, tstep, ttotal, rtol=1e-6, atol=1e-6, min
                            float(ttotal), float(rtol), float(atol), float(min_step_factor), float(cut_off),
                            _p(out), _p(acc, _ip), _p(att, _ip))
     return acc.reshape(shp), att.reshape(shp)
+
+
+def ray_run_rk4(fields, lon, lat, out, tstep, cut_off=0.1):
+    """wr.py:702-765 (fixed-step RK4, the reference's default inte_method='') in place on `out`."""
+    fields = _f64(fields); lon = _f64(lon); lat = _f64(lat)
+    assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape[0] == 7
+    nt = out.shape[1]
+    N = int(np.prod(out.shape[2:]))
+    lib().orc_ray_run_rk4(fields.shape[0], fields.shape[1], _p(fields), _p(lon), _p(lat), N, nt, float(tstep),
+                          float(cut_off), _p(out))
+    return out
 
 
 def kat(kind, y0, t_end, rtol, atol, gmin):

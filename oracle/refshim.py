@@ -124,3 +124,15 @@ def run_rk45(w, quiet=True):
     out["accepted"] = acc.reshape(3, w.nsource, w.nzwn)
     out["passes"] = sc.passes
     return out
+
+
+def run_rk4(w, quiet=True):
+    """`WR.ray_run(mode='numpy', root_method='numpy', inte_method='')`: the fixed-step RK4 path (wr.py:702-765).
+    `accepted` is the number of output intervals (every slot takes nt-1 fixed steps)."""
+    ctx = contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext()
+    with ctx:
+        w.ray_run(mode="numpy", root_method="numpy", inte_method="")
+    out = {k: getattr(w, k).copy() for k in ("rlon", "rlat", "rzwn", "rmwn", "ramp", "rug", "rvg")}
+    out["accepted"] = np.full((3, w.nsource, w.nzwn), w.nt - 1, dtype=np.int64)
+    out["passes"] = w.nt - 1
+    return out

@@ -596,6 +596,69 @@ int orc_ray_run_rk45(int nlon_f, int nlat, const double *fields, const double *l
     return 0;
 }
 
+/*
+ * wr.py:702-765 core_ray_run_numpy + wr.py:583-622 rk4_step_numpy + wr.py:89-95 core_rk4_step: the
+ * fixed-step RK4 path (inte_method='' -- main_wr.py's default), one ray at a time.  State is the five
+ * integrated components; ug / vg of the stored rows are the fresh-sample values (wr.py:737-756), the
+ * step-averaged ug / vg of core_rk4_step never reach the outputs.
+ * "Freeze" semantics: if the ray is valid at the step start (mask1 false) but a later stage input hits the
+ * |lat| >= pi/2 / |l| >= 100 mask, the step is not taken and the old state is kept (wr.py:608-618).
+ * NaN-root slots are NOT masked (comparisons with NaN are False): their step gives NaN in all components.
+ */
+static int rhs_masked(const orc_grid *g, const double *y, double *dy)
+{
+    int err = (fabs(y[1]) >= 0.5 * RWRT_PI) || (fabs(y[3]) >= 100.0); /* wr.py:508-510 */
+    rhs(g, y, dy);
+    return err;
+}
+
+int orc_ray_run_rk4(int nlon_f, int nlat, const double *fields, const double *lon, const double *lat, int64_t N,
+                    int nt, double tstep, double cut_off_factor, double *out)
+{
+    orc_grid g = {nlon_f, nlat, fields, lon[0], lon[1] - lon[0], lat[0], lat[1] - lat[0]};
+    double cut = cut_off_factor * tstep / 3600.;
+    double dt = tstep;
+    size_t pl = (size_t)nt * N;
+    double *pln[7];
+    for (int k = 0; k < 7; ++k) pln[k] = out + k * pl;
+    for (int64_t r = 0; r < N; ++r) {
+        double y[5];
+        for (int c = 0; c < 5; ++c) y[c] = pln[c][r];
+        double plon = y[0], plat = y[1];
+        for (int it = 0; it < nt - 1; ++it) {
+            double k1[5], k2[5], k3[5], k4[5], ys[5], yn[5];
+            int m1 = rhs_masked(&g, y, k1);
+            for (int c = 0; c < 5; ++c) yn[c] = y[c];
+            if (!m1) {
+                for (int c = 0; c < 5; ++c) ys[c] = y[c] + 0.5 * dt * k1[c];
+                int m2 = rhs_masked(&g, ys, k2);
+                for (int c = 0; c < 5; ++c) ys[c] = y[c] + 0.5 * dt * k2[c];
+                int m3 = rhs_masked(&g, ys, k3);
+                for (int c = 0; c < 5; ++c) ys[c] = y[c] + dt * k3[c];
+                int m4 = rhs_masked(&g, ys, k4);
+                if (!m2 && !m3 && !m4)
+                    for (int c = 0; c < 5; ++c) /* wr.py:92-93 */
+                        yn[c] = y[c] + (dt / 6.0) * (k1[c] + 2 * k2[c] + 2 * k3[c] + k4[c]);
+            }
+            if (fabs(yn[1]) >= 0.5 * RWRT_PI)                  /* wr.py:721-726 */
+                for (int c = 0; c < 5; ++c) yn[c] = NAN;
+            double dd = haversine(yn[0], yn[1], plon, plat);   /* wr.py:728-734 */
+            if (fabs(dd) >= cut)
+                for (int c = 0; c < 5; ++c) yn[c] = NAN;
+            double m[12], ug, vg;
+            sample_mercator(&g, yn[0], yn[1], m);              /* wr.py:737-746 */
+            ugvg_extent(m[0], m[1], m[6], m[7], yn[2], yn[3], &ug, &vg);
+            size_t o = (size_t)(it + 1) * N + r;
+            for (int c = 0; c < 5; ++c) { pln[c][o] = yn[c]; y[c] = yn[c]; }
+            pln[5][o] = ug;
+            pln[6][o] = vg;
+            plon = yn[0];
+            plat = yn[1];
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* Known-answer ODEs of rkf45.py's __main__ demo (rkf45.py:772-882): the solver alone      */
 /* ------------------------------------------------------------------------------------ */

@@ -604,6 +604,34 @@ int host_copy_hook(void *vctx, int it_begin, int it_end, cudaStream_t s)
 }
 }  // namespace
 
+int rwrt_ray_run_rk4(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep, double cut_off,
+                     uint32_t flags, double *out7, int8_t *status, void *stream)
+{
+    if (!h || nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk4: bad sizes");
+    if (!(tstep > 0)) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk4: tstep must be positive");
+    if (!h->ready) return fail(RWRT_ERR_STATE, "rwrt_ray_run_rk4 before rwrt_bs_ready");
+    long long N = 3LL * nsource * nzwn;
+    if (N == 0 || nt < 2) return RWRT_OK;
+    if (!out7) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk4: out7 is NULL");
+    CU(cudaSetDevice(h->device));
+    RunParams p;
+    memset(&p, 0, sizeof p);
+    p.g = h->grid();
+    p.src_member = src_member;
+    p.nsource = nsource;
+    p.nzwn = nzwn;
+    p.nt = nt;
+    p.N = N;
+    p.tstep = tstep;
+    p.cut = cut_off * tstep / 3600.;  // wr.py:170
+    p.out = out7;
+    p.status = (signed char *)status;
+    if (flags & RWRT_MODE_STRICT) launch_rk4_strict(p, (cudaStream_t)stream);
+    else launch_rk4_fast(p, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return RWRT_OK;
+}
+
 int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
                           double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
                           double *out7, int64_t *accepted, int64_t *attempts, int8_t *status, int64_t *total_accepted,

@@ -14,6 +14,8 @@ void launch_rk45_setup_fast(const RunParams &p, int prepare_blocks, int fill_blo
 void launch_rk45_setup_strict(const RunParams &p, int prepare_blocks, int fill_blocks, cudaStream_t s, cudaStream_t aux);
 void launch_rk45_window_fast(const RunParams &p, int integrate_blocks, cudaStream_t s);
 void launch_rk45_window_strict(const RunParams &p, int integrate_blocks, cudaStream_t s);
+void launch_rk4_fast(const RunParams &p, cudaStream_t s);
+void launch_rk4_strict(const RunParams &p, cudaStream_t s);
 int occupancy_rk45_fast(bool coop);
 int occupancy_rk45_strict(bool coop);
 void launch_build_cells(const Grid &g, int nmember, double *fcell, cudaStream_t s);

@@ -708,5 +708,68 @@ __global__ void __launch_bounds__(256) build_cells_kernel(Grid g, int nmember, d
     for (int k = 44; k < NCELL; ++k) o[k] = 0.0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-step RK4 path: WR.core_ray_run_numpy (wr.py:702-765) with rk4_step_numpy (wr.py:583-622) and
+// core_rk4_step (wr.py:89-95) -- the reference's DEFAULT integrator (inte_method='').  One slot per
+// thread, every thread takes the same nt-1 steps, so rows are written fully coalesced; all slots run
+// (NaN-root slots are not masked by the reference and turn all-NaN at row 1).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rk4_integrate(RunParams p)
+{
+    long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= p.N) return;
+    const size_t pl = (size_t)p.nt * p.N;
+    const double *fb = member_base(p, slot);
+    double y[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) y[c] = p.out[c * pl + slot];
+    double plon = y[0], plat = y[1];
+    const double dt = p.tstep;
+    int code = (y[3] == y[3]) ? 1 : 0;
+    for (int it = 0; it < p.nt - 1; ++it) {
+        double k1[5], k2[5], k3[5], k4[5], ys[5], yn[5], ug, vg;
+        bool m1, m2, m3, m4;
+        ray_rhs<RWRT_FAST>(p.g, fb, y, k1, ug, vg, m1);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) yn[c] = y[c];
+        if (!m1) {  // wr.py:598-618
+#pragma unroll
+            for (int c = 0; c < 5; ++c) ys[c] = y[c] + 0.5 * dt * k1[c];
+            ray_rhs<RWRT_FAST>(p.g, fb, ys, k2, ug, vg, m2);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) ys[c] = y[c] + 0.5 * dt * k2[c];
+            ray_rhs<RWRT_FAST>(p.g, fb, ys, k3, ug, vg, m3);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) ys[c] = y[c] + dt * k3[c];
+            ray_rhs<RWRT_FAST>(p.g, fb, ys, k4, ug, vg, m4);
+            if (!m2 && !m3 && !m4) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) yn[c] = y[c] + (dt / 6.0) * (k1[c] + 2 * k2[c] + 2 * k3[c] + k4[c]);
+            }
+        }
+        if (fabs(yn[1]) >= HALFPI) {  // wr.py:721-726
+#pragma unroll
+            for (int c = 0; c < 5; ++c) yn[c] = qnan();
+            if (code == 1) code = 2;
+        }
+        double dd = haversine(yn[0], yn[1], plon, plat);  // wr.py:728-734
+        if (fabs(dd) >= p.cut) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) yn[c] = qnan();
+            if (code == 1) code = 3;
+        }
+        if (code == 1 && !(yn[0] + yn[1] + yn[2] + yn[3] + yn[4] == yn[0] + yn[1] + yn[2] + yn[3] + yn[4])) code = 4;
+        Merc m = sample_mercator<RWRT_FAST>(p.g, fb, yn[0], yn[1]);  // wr.py:737-746
+        ugvg_extent(m.u, m.v, m.qx, m.qy, yn[2], yn[3], ug, vg);
+        write_row(p, slot, it + 1, yn[0], yn[1], yn[2], yn[3], yn[4], ug, vg);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) y[c] = yn[c];
+        plon = yn[0];
+        plat = yn[1];
+    }
+    if (p.status) p.status[slot] = (signed char)code;
+}
+
 }  // namespace RWRT_VARIANT
 }  // namespace rwrt

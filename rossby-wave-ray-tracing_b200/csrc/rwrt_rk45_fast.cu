@@ -23,6 +23,11 @@ void launch_rk45_window_fast(const RunParams &p, int integrate_blocks, cudaStrea
     else
         fast::rk45_integrate<<<integrate_blocks, fast::RK_THREADS, fast::RK_SMEM_BYTES, s>>>(p);
 }
+void launch_rk4_fast(const RunParams &p, cudaStream_t s)
+{
+    if (p.N > 0 && p.nt > 1) fast::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+}
+
 int occupancy_rk45_fast(bool coop)
 {
     int nb = 0;

@@ -23,6 +23,11 @@ void launch_rk45_window_strict(const RunParams &p, int integrate_blocks, cudaStr
     else
         strict::rk45_integrate<<<integrate_blocks, strict::RK_THREADS, strict::RK_SMEM_BYTES, s>>>(p);
 }
+void launch_rk4_strict(const RunParams &p, cudaStream_t s)
+{
+    if (p.N > 0 && p.nt > 1) strict::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+}
+
 int occupancy_rk45_strict(bool coop)
 {
     int nb = 0;

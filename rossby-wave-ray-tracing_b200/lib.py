@@ -20,7 +20,7 @@ RAY_NO_ROOT, RAY_ALIVE, RAY_POLE, RAY_SPEED, RAY_NAN = 0, 1, 2, 3, 4
 SYMBOLS = (
     "rwrt_abi_version", "rwrt_last_error", "rwrt_device_count", "rwrt_host_alloc", "rwrt_host_free",
     "rwrt_create", "rwrt_destroy", "rwrt_bs_ready", "rwrt_bs_set_fields", "rwrt_sample_mercator", "rwrt_rhs",
-    "rwrt_ray_init", "rwrt_ray_run_rk45", "rwrt_ray_run_rk45_d2h", "rwrt_grid_accumulate", "rwrt_real2d_host", "rwrt_last_run_stats", "rwrt_measure_fp64_peak",
+    "rwrt_ray_init", "rwrt_ray_run_rk45", "rwrt_ray_run_rk45_d2h", "rwrt_ray_run_rk4", "rwrt_grid_accumulate", "rwrt_real2d_host", "rwrt_last_run_stats", "rwrt_measure_fp64_peak",
 )
 
 
@@ -56,6 +56,7 @@ def load():
     L.rwrt_ray_init.argtypes = [vp, i32, vp, vp, vp, i32, vp, f64, i32, vp, vp]
     L.rwrt_ray_run_rk45.argtypes = [vp, i32, vp, i32, i32, f64, f64, f64, f64, f64, f64, u32, vp, vp, vp, vp, vp, vp]
     L.rwrt_ray_run_rk45_d2h.argtypes = [vp, i32, vp, i32, i32, f64, f64, f64, f64, f64, f64, u32, vp, vp, vp, vp, vp, vp, vp]
+    L.rwrt_ray_run_rk4.argtypes = [vp, i32, vp, i32, i32, f64, f64, u32, vp, vp, vp]
     L.rwrt_grid_accumulate.argtypes = [vp, i64, i32, vp, f64, f64, i32, i32, vp, vp, vp, vp]
     L.rwrt_real2d_host.argtypes = ([vp] + [vp] * 6 + [i32, vp, vp, vp, i32, vp, f64, i32] + [f64] * 6 +
                                    [u32, vp, vp, vp, vp, vp])

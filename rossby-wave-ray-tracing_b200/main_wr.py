@@ -1,9 +1,9 @@
 """Driver entry with the reference's signature: `real2d_hnf(**parameters)` (`main_wr.py:5-100`).
 
 Same dict keys, same call sequence (WR -> loadbs_ncfile -> ready -> output -> set_zwn ->
-set_source_matrix -> ray_info -> ray_run -> output).  `mode='numpy', inte_method='rk45'` selects
-the GPU engine; the reference's default `inte_method=''` (fixed-step RK4) is not implemented here
-and raises — there is no CPU fallback.
+set_source_matrix -> ray_info -> ray_run -> output).  `mode='numpy'` runs on the GPU with
+`inte_method='rk45'` (adaptive RK45, the hot path) or `''` (fixed-step RK4, the reference's default);
+`mode='original'` raises — there is no CPU fallback.
 """
 import numpy as np
 
@@ -20,7 +20,7 @@ parameters = {
     'ttotal': 90.,
     'mode': 'numpy',
     'root_method': 'numpy',
-    'inte_method': 'rk45',   # the reference defaults to '' (RK4); the GPU engine is the RK45 path
+    'inte_method': 'rk45',   # '' = fixed-step RK4 (the reference's default), 'rk45' = adaptive
     'xcyclic': True,
     'cal_dtype': 'float64',
     'read_dtype': 'float32',

@@ -168,24 +168,45 @@ class WR:
             _lib.check(_lib.load().rwrt_ray_run_rk45(*args, _lib.stream_ptr()), "rwrt_ray_run_rk45")
         return False
 
+    def core_ray_run_rk4(self, strict=False):
+        """wr.py:702-765 (mode 'numpy'): fixed-step RK4, the reference's default integrator."""
+        import torch
+        dev = torch.device("cuda", self.bs.device)
+        N = 3 * self.nsource * self.nzwn
+        self._d_status = torch.zeros(N, dtype=torch.int8, device=dev)
+        flags = _lib.MODE_STRICT if strict else _lib.MODE_FAST
+        with torch.cuda.device(self.bs.device):
+            _lib.check(_lib.load().rwrt_ray_run_rk4(self.bs._h, self.nsource, None, self.nzwn, self.nt,
+                                                    float(self.tstep[0]), float(self.cut_off_factor), flags,
+                                                    _lib.ptr(self.d_out), _lib.ptr(self._d_status), _lib.stream_ptr()),
+                       "rwrt_ray_run_rk4")
+
     def ray_run(self, mode="original", inte_method="", root_method="Fortran", debug=False, debug_file=None,
                 to_host=True, strict=False):
-        """wr.py:897-911.  `mode='numpy', inte_method='rk45'` is the path the GPU engine replaces."""
-        if mode != "numpy" or inte_method != "rk45":
+        """wr.py:897-911.  mode='numpy' with inte_method='rk45' (adaptive RK45) or anything else (fixed-step
+        RK4, the reference's default) run on the GPU; the scalar mode='original' does not exist here."""
+        if mode != "numpy":
             raise NotImplementedError(
-                "rwrt_b200 implements ray_run(mode='numpy', inte_method='rk45') only; the reference's "
-                "scalar 'original' mode and fixed-step RK4 are not part of the GPU path and there is no CPU fallback")
+                "rwrt_b200 implements ray_run(mode='numpy', ...) only; the reference's scalar 'original' mode is "
+                "not part of the GPU path and there is no CPU fallback")
         if debug:
             raise NotImplementedError("debug / debug_file (Fortran parity hooks, wr.py:901-906) are not supported")
-        self.ray_initial(mode="numpy", root_method=root_method)
-        if to_host:
-            self._host_planes()          # the (pinned) result arrays exist before the run
-        delivered = self.core_ray_run("numpy_rk45", strict=strict, to_host=to_host)
         import torch
-        torch.cuda.synchronize(self.bs.device)
+        self.ray_initial(mode="numpy", root_method=root_method)
         shp = (3, self.nsource, self.nzwn)
-        self.total_accepted = int(self._d_total.item())
-        self.accepted = self._d_acc.cpu().numpy().reshape(shp)
+        if inte_method == "rk45":                                       # wr.py:907-908
+            if to_host:
+                self._host_planes()          # the (pinned) result arrays exist before the run
+            delivered = self.core_ray_run("numpy_rk45", strict=strict, to_host=to_host)
+            torch.cuda.synchronize(self.bs.device)
+            self.total_accepted = int(self._d_total.item())
+            self.accepted = self._d_acc.cpu().numpy().reshape(shp)
+        else:
+            delivered = False
+            self.core_ray_run_rk4(strict=strict)
+            torch.cuda.synchronize(self.bs.device)
+            self.total_accepted = 0
+            self.accepted = None
         self.status = self._d_status.cpu().numpy().reshape(shp)
         if to_host and not delivered:
             self.to_host()

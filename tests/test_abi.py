@@ -85,7 +85,7 @@ def test_wr_host_logic_matches_reference_semantics():
 
 def test_ray_run_rejects_non_gpu_paths():
     w = WR(1, 1, 7200.0, 86400.0, nx=144, ny=73)
-    for kw in (dict(mode="original"), dict(mode="numpy", inte_method=""), dict(mode="numpy", inte_method="rk4")):
+    for kw in (dict(mode="original"), dict(mode="original", inte_method="rk45"), dict(mode="numpy", debug=True)):
         with pytest.raises(NotImplementedError):
             w.ray_run(**kw)
 

@@ -247,8 +247,6 @@ def test_empty_and_error_paths():
     w.ray_run(mode="numpy", inte_method="rk45")
     assert w.rlon.shape == (25, 3, 0, 2) and w.total_accepted == 0
     with pytest.raises(NotImplementedError):
-        w.ray_run(mode="numpy", inte_method="")
-    with pytest.raises(NotImplementedError):
         w.ray_run(mode="original", inte_method="rk45")
     L = lib.load()
     h = lib.vp()
@@ -380,3 +378,21 @@ def test_frequency_sweep_with_gridding():
             assert not np.array_equal(first_l0, w.rmwn[0], equal_nan=True)   # omega changes the roots
         total = ref[0] if total is None else total + ref[0]
     assert total.sum() > 1e5
+
+
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+@pytest.mark.parametrize("name", ["rk4_jet", "rk4_clim_g1"])
+def test_rk4_path_vs_reference(name, strict):
+    """rwrt_ray_run_rk4 vs wr.py:702-765 on the reference's outputs (main_wr.py's default inte_method='')."""
+    g = parity.load(name)
+    u, v = parity.background(g)
+    w = make_wr(u, v, g["zwn"], g["src_lon_rad"], g["src_lat_rad"], float(g["days"]), float(g["freq"]),
+                float(g["tstep_h"]))
+    w.ray_run(mode="numpy", root_method="numpy", inte_method="", strict=strict)
+    got = {n: getattr(w, n) for n in parity.NAMES}
+    ref = {n: g[n] for n in parity.NAMES}
+    st = parity.compare(got, None, ref, g["accepted"], g["nongrazing"], name)
+    assert w.accepted is None and w.total_accepted == 0
+    dead = np.isnan(g["rmwn"][0])
+    assert np.isnan(w.rlon[1:, dead]).all()
+    print(name, st)

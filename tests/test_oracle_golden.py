@@ -189,3 +189,25 @@ def test_great_circle_known_answer():
                 nrm = np.cross(p[0], p[5])
                 nrm /= np.linalg.norm(nrm)
                 assert np.max(np.abs(p @ nrm)) < 5e-3
+
+
+@pytest.mark.parametrize("name", ["rk4_jet", "rk4_clim_g1"])
+def test_rk4_path_vs_reference(name):
+    """wr.py:702-765 (inte_method='', the reference's default): fixed-step RK4 with freeze-on-failure;
+    NaN-root slots turn all-NaN at row 1 (they are not masked by wr.py:508-510)."""
+    g = parity.load(name)
+    u, v = parity.background(g)
+    lon, lat = synthetic.grid_coords(*u.shape)
+    F = oracle.bs_ready(u, v, lat, True)
+    nt = g["rlon"].shape[0]
+    out = oracle.ray_init(F, lon, lat, g["src_lon_rad"], g["src_lat_rad"], g["zwn"], float(g["freq"]), nt)
+    oracle.ray_run_rk4(F, lon, lat, out, float(g["tstep_h"]) * 3600.0)
+    got = {n: out[k] for k, n in enumerate(parity.NAMES)}
+    ref = {n: g[n] for n in parity.NAMES}
+    parity.compare(got, None, ref, g["accepted"], g["nongrazing"], name)
+    dead = np.isnan(g["rmwn"][0])
+    assert np.isnan(out[0][1:, dead]).all()            # NaN-root slots: everything NaN from row 1
+    # on this path the C restatement reproduces the reference's positions bit for bit and the rest to 1e-12
+    assert np.array_equal(out[0], g["rlon"], equal_nan=True) and np.array_equal(out[1], g["rlat"], equal_nan=True)
+    for k, n in enumerate(parity.NAMES):
+        np.testing.assert_allclose(out[k], g[n], rtol=1e-12, atol=1e-300, equal_nan=True, err_msg=n)
