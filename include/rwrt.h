@@ -96,6 +96,11 @@ int rwrt_bs_set_fields(rwrt_handle h, const double *fields18, const double *lon,
 int rwrt_sample_mercator(rwrt_handle h, int64_t n, const double *lon, const double *lat, const int32_t *member,
                          double *out, void *stream);
 
+/* All 18 rows of BS.cal_bs_mercator_point (bs.py:856-887), sampled from a fields18 table as written by
+ * rwrt_bs_ready (rows 12..17 are the third-derivative terms the ray path never consumes).  out: (18, n). */
+int rwrt_sample_mercator18(rwrt_handle h, const double *fields18, int64_t n, const double *lon, const double *lat,
+                           const int32_t *member, double *out, void *stream);
+
 /* One right-hand side per point: WR.diffun_numpy (wr.py:492-556).  y, dy: (5, n). */
 int rwrt_rhs(rwrt_handle h, int64_t n, const double *y, const int32_t *member, double *dy, uint32_t flags,
              void *stream);

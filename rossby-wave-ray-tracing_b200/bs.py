@@ -140,8 +140,8 @@ class BS:
 
     # ---- BS.cal_bs_mercator_point (bs.py:513-887) ------------------------------------------
     def cal_bs_mercator_point(self, lon, lat, mode="numpy"):
-        """Rows 0..11 = fmu, fmv, fmux, fmuy, fmvx, fmvy, fmqx, fmqy, fmqxx, fmqxy, fmqyx, fmqyy as in
-        the reference; rows 12..17 (third-derivative terms, never consumed by the ray path) are NaN."""
+        """The reference's 18 rows (fmu ... fmqyy, fmqxxx ... fmqyyx) at the given points.  When ready() was
+        called with keep_fields18=False only rows 0..11 (what the ray path consumes) are computed; 12..17 are NaN."""
         if mode != "numpy":
             raise NotImplementedError("only mode='numpy' (the vectorised path) exists on the GPU engine")
         if self._h is None:
@@ -154,8 +154,13 @@ class BS:
         dl, da = torch.from_numpy(lon).to(dev), torch.from_numpy(lat).to(dev)
         out = torch.full((18, n), float("nan"), dtype=torch.float64, device=dev)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.load().rwrt_sample_mercator(self._h, n, _lib.ptr(dl), _lib.ptr(da), None, _lib.ptr(out),
-                                                        _lib.stream_ptr()), "rwrt_sample_mercator")
+            if self._d.get("fields18") is not None:
+                _lib.check(_lib.load().rwrt_sample_mercator18(self._h, _lib.ptr(self._d["fields18"]), n, _lib.ptr(dl),
+                                                              _lib.ptr(da), None, _lib.ptr(out), _lib.stream_ptr()),
+                           "rwrt_sample_mercator18")
+            else:
+                _lib.check(_lib.load().rwrt_sample_mercator(self._h, n, _lib.ptr(dl), _lib.ptr(da), None,
+                                                            _lib.ptr(out), _lib.stream_ptr()), "rwrt_sample_mercator")
         return out.cpu().numpy()
 
     def output(self, ncfile):

@@ -382,6 +382,18 @@ int rwrt_sample_mercator(rwrt_handle h, int64_t n, const double *lon, const doub
     return RWRT_OK;
 }
 
+int rwrt_sample_mercator18(rwrt_handle h, const double *fields18, int64_t n, const double *lon, const double *lat,
+                           const int32_t *member, double *out, void *stream)
+{
+    if (!h || !fields18 || (n > 0 && (!lon || !lat || !out)))
+        return fail(RWRT_ERR_ARG, "rwrt_sample_mercator18: NULL argument");
+    if (!h->ready) return fail(RWRT_ERR_STATE, "rwrt_sample_mercator18 before rwrt_bs_ready");
+    CU(cudaSetDevice(h->device));
+    launch_sample18(h->grid(), fields18, n, lon, lat, member, out, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return RWRT_OK;
+}
+
 int rwrt_rhs(rwrt_handle h, int64_t n, const double *y, const int32_t *member, double *dy, uint32_t flags, void *stream)
 {
     if (!h || (n > 0 && (!y || !dy))) return fail(RWRT_ERR_ARG, "rwrt_rhs: NULL argument");

@@ -428,7 +428,63 @@ __global__ void __launch_bounds__(128) sample_kernel(Grid g, long long n, const 
     out[11 * n + i] = m.qyy;
 }
 
+// All 18 rows of BS.cal_bs_mercator_point(mode='numpy') (bs.py:781-887) from the reference-layout fields18
+// table (nlon_f, nlat, 18): rows 12..17 are the third-derivative terms the ray path never consumes.
+__global__ void __launch_bounds__(128) sample18_kernel(Grid g, const double *f18, size_t member_stride18, long long n,
+                                                       const double *lon, const double *lat, const int32_t *member,
+                                                       double *out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double la = lat[i];
+    if (!(fabs(la) <= HALFPI)) {  // bs.py:787
+        for (int k = 0; k < 18; ++k) out[(size_t)k * n + i] = qnan();
+        return;
+    }
+    const double *fb = f18 + (member ? (size_t)member[i] * member_stride18 : 0);
+    int x0, y0, x1, y1;
+    double sx, sy;
+    locate<false>(g, lon[i], la, x0, y0, x1, y1, sx, sy);
+    const int H = g.nlat;
+    double wa = (1 - sx) * sy, wb = sx * sy, wc = (1 - sx) * (1 - sy), wd = sx * (1 - sy);
+    const double *pa = fb + ((size_t)x0 * H + y1) * 18, *pb = fb + ((size_t)x1 * H + y1) * 18;
+    const double *pc = fb + ((size_t)x0 * H + y0) * 18, *pd = fb + ((size_t)x1 * H + y0) * 18;
+    double f[18];
+    for (int k = 0; k < 18; ++k) f[k] = pa[k] * wa + pb[k] * wb + pc[k] * wc + pd[k] * wd;
+    double cp = cos(la), sp = sin(la), tl = tan(la);
+    double mask = (fabs(cp) <= 0.0175) ? 0.0 : 1.0;  // bs.py:858-860
+    cp = cp * mask + (1 - mask) * 1e-6;
+    double o[18];
+    o[8] = f[8] * mask;                               // fmqxx
+    o[10] = f[9] * cp * mask;                         // fmqyx
+    o[9] = o[10] * mask;                              // fmqxy
+    o[11] = (f[11] * cp - f[7] * sp) * cp * mask;     // fmqyy
+    o[12] = f[12] * mask;                             // fmqxxx
+    o[13] = f[13] * cp * mask;                        // fmqxxy
+    o[14] = (f[14] * cp - f[9] * sp) * cp * mask;     // fmqxyy
+    o[15] = f[15] * mask;                             // fmqyyy
+    o[16] = f[16] * cp * mask;                        // fmqyxx
+    o[17] = (f[17] * cp - f[9] * sp) * cp * mask;     // fmqyyx
+    o[6] = f[6] * mask;                               // fmqx
+    o[7] = f[7] * cp * mask;                          // fmqy
+    o[2] = f[2] / cp * mask;                          // fmux
+    o[4] = f[4] / cp * mask;                          // fmvx
+    o[3] = (f[3] + tl * f[0]) * mask;                 // fmuy
+    o[5] = (f[5] + tl * f[1]) * mask;                 // fmvy
+    o[0] = f[0] / cp * mask;                          // fmu
+    o[1] = f[1] / cp * mask;                          // fmv
+    for (int k = 0; k < 18; ++k) out[(size_t)k * n + i] = o[k];
+}
+
 }  // namespace
+
+void launch_sample18(const Grid &g, const double *f18, long long n, const double *lon, const double *lat,
+                     const int32_t *member, double *out, cudaStream_t s)
+{
+    if (n > 0)
+        sample18_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, f18, (size_t)g.nlon_f * g.nlat * 18, n, lon, lat,
+                                                                    member, out);
+}
 
 void launch_ray_init(const Grid &g, int nsource, const double *src_lon, const double *src_lat, const int32_t *src_member,
                      int nzwn, const double *zwn, double freq, int nt, double *out7, cudaStream_t s)

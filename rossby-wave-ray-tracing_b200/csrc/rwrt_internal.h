@@ -42,6 +42,9 @@ void launch_ray_init(const Grid &g, int nsource, const double *src_lon, const do
 void launch_sample_mercator(const Grid &g, long long n, const double *lon, const double *lat, const int32_t *member,
                             double *out, cudaStream_t s);
 
+void launch_sample18(const Grid &g, const double *f18, long long n, const double *lon, const double *lat,
+                     const int32_t *member, double *out, cudaStream_t s);
+
 // rwrt_grid.cu
 void launch_grid_accumulate(long long nslot, int nt, const double *out7, double dlon_deg, double dlat_deg, int ncx,
                             int ncy, long long *count, long long *fx, long long *fy, cudaStream_t s);

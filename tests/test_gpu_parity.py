@@ -80,11 +80,13 @@ def test_sampler_rhs_vs_reference():
     g = parity.load("pointwise")
     u, v = synthetic.clim(144, 73)
     w = make_wr(u, v, [1.0], [0.1], [0.1], 1.0)
-    got = w.bs.cal_bs_mercator_point(g["plon"], g["plat"], mode="numpy")[:12].T
-    ref = g["merc"]
-    assert np.array_equal(np.isnan(got), np.isnan(ref))
-    ok = np.isfinite(ref)
-    assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-6)) < 1e-8
+    got18 = w.bs.cal_bs_mercator_point(g["plon"], g["plat"], mode="numpy").T      # all 18 rows (bs.py:884-887)
+    ref18 = g["merc18"]
+    assert got18.shape == ref18.shape == (len(g["plon"]), 18)
+    assert np.array_equal(np.isnan(got18), np.isnan(ref18))
+    ok = np.isfinite(ref18)
+    assert np.max(np.abs(got18[ok] - ref18[ok]) / np.maximum(np.abs(ref18[ok]), 1e-6)) < 1e-8
+    got, ref = got18[:, :12], g["merc"]
     y = torch.from_numpy(np.ascontiguousarray(g["y"].T)).cuda()       # (5, n)
     for flags in (lib.MODE_FAST, lib.MODE_STRICT):
         dy = torch.empty_like(y)
