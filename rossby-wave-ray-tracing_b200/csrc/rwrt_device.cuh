@@ -144,6 +144,33 @@ __device__ __forceinline__ void sincos_halfpi(double x, double &sn, double &cs)
     cs = (q == 0.0) ? cr : ((q > 0.0) ? -sr : sr);
 }
 
+// FAST-build sine of a small angle (the speed cut-off's sin(dlat/2), sin(dlon/2)): the fdlibm kernel polynomial
+// on |x| <= pi/4, the library routine beyond (rare: such a ray has moved > 90 degrees in one output interval).
+__device__ __forceinline__ double sin_small(double x)
+{
+    if (!(fabs(x) <= 0.78539816339744830962)) return sin(x);
+    const double z = x * x;
+    double ps = fma(z, cSinCos[5], cSinCos[4]);
+    ps = fma(z, ps, cSinCos[3]);
+    ps = fma(z, ps, cSinCos[2]);
+    ps = fma(z, ps, cSinCos[1]);
+    ps = fma(z, ps, cSinCos[0]);
+    return fma(x * z, ps, x);
+}
+
+// FAST-build reciprocal: hardware seed (MUFU.RCP64H, ~2^-20) + two Newton steps, no special-case branch
+// (0 -> inf, like the division it replaces; the operands here are never denormal).
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
 // FAST-build err^(-1/5) for the step controller (rkf45.py:453-455, 474-475): float seed + two Newton
 // steps y <- y (6 - a y^5) / 5 in double (quadratic: 2^-21 -> 2^-42 -> full), instead of the 166-instruction pow().
 __device__ __forceinline__ double pow_m02(double a)
@@ -169,7 +196,7 @@ __device__ __forceinline__ Trig trig_of_lat(double lat)
     t.rc = 0.0;
     if (FAST) {
         sincos_halfpi(lat, t.sp, t.cp);
-        t.rc = 1.0 / t.cp;
+        t.rc = rcp_fast(t.cp);
         t.tl = t.sp * t.rc;
     } else {
         t.cp = cos(lat);
@@ -277,7 +304,7 @@ __device__ __forceinline__ WaveRecip wave_recip(double kx, double ky)
     WaveRecip w;
     double k2 = kx * kx, l2 = ky * ky;
     double K2 = k2 + l2;                 // = kk = kx^2 (1 + kap^2)
-    double r = 1.0 / (kx * K2 * K2);     // one reciprocal for 1/kx, 1/kk, 1/kap1, 1/(kk kap1)
+    double r = rcp_fast(kx * K2 * K2);   // one reciprocal for 1/kx, 1/kk, 1/kap1, 1/(kk kap1)
     double rk = r * K2 * K2;             // 1/kx
     w.kap = ky * rk;
     w.kap2 = w.kap * w.kap;
@@ -380,7 +407,7 @@ __device__ __forceinline__ double haversine(double lon_c, double lat_c, double l
 __device__ __forceinline__ bool speed_cutoff_fast(double lon_c, double lat_c, double lon_p, double lat_p, double cos_c,
                                                   double cos_p, double sin2_half_cut)
 {
-    double s1 = sin((lat_c - lat_p) / 2.0), s2 = sin((lon_c - lon_p) / 2.0);
+    double s1 = sin_small((lat_c - lat_p) * 0.5), s2 = sin_small((lon_c - lon_p) * 0.5);
     double a = s1 * s1 + cos_p * cos_c * (s2 * s2);
     return a >= sin2_half_cut;
 }

@@ -392,13 +392,15 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
 // its own 4 corners x 96 B with 24 fully divergent LDG.128 per right-hand side.  Here the warp
 // fetches together: each ray's bilinear cell is ONE 384-byte record (11 fields x 4 corners, 3 cache
 // lines, line aligned), a quarter-warp copies one line of one ray with 8 contiguous 16-byte
-// cp.async (LDGSTS) -- 4 wavefronts per instruction instead of ~32 -- straight into a swizzled
+// cp.async (LDGSTS) -- 4 wavefronts per instruction instead of ~32 -- straight into a padded
 // shared-memory stage (no landing registers, all 24 copies of a stage in flight at once), and while
 // they fly the lanes evaluate sincos / the wavenumber reciprocals.  Each lane then reads its own
 // record back with conflict-free LDS.128.  Arithmetic and operation order are unchanged.
-// Shared memory per warp: 12 KB stage + 6.25 KB for K2..K6 -> 3 blocks of 128 threads per SM.
+// Shared memory per warp: 11.75 KB stage + 6.25 KB for K2..K6 -> 3 blocks of 128 threads per SM.
 // ---------------------------------------------------------------------------------------------
-constexpr int CO_STAGE_BYTES = 32 * 384;                                   // per warp
+constexpr int CO_REC_STRIDE = 368;   // 23 x 16 B per staged ray: chunk q of ray r sits in bank group (q - r) mod 8,
+                                     // so a quarter-warp's LDS.128 / LDGSTS never conflict -- no swizzle arithmetic
+constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE + 256;                   // per warp: records + 32 record pointers
 constexpr int CO_SMEM_BYTES = (RK_THREADS / 32) * CO_STAGE_BYTES + 5 * 5 * RK_THREADS * (int)sizeof(double);
 
 __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src)
@@ -433,11 +435,8 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
     long long my_ray = -1;                                                 // index of this lane's ray in the state array
     int acc0 = 0;                                                          // accepted steps when this launch picked the ray up
     const double shc = sin(0.5 * p.cut), sin2_half_cut = (p.cut >= PI) ? 2.0 : shc * shc;  // angle <= pi: never cut
-    // own-record read offsets: logical 16-byte chunk q of ray r lives at r*384 + (q>>3)*128 + ((q&7)^(r&7))*16
-    const unsigned char *my_rec = stage + lane_id * 384;
-    int swz[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) swz[j] = (j ^ (lane_id & 7)) << 4;
+    const unsigned char *my_rec = stage + lane_id * CO_REC_STRIDE;        // this lane's staged cell record
+    const double **recptr = reinterpret_cast<const double **>(stage + 32 * CO_REC_STRIDE);  // [32] per warp
 
     for (;;) {
         __syncwarp();
@@ -526,13 +525,14 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             prev_rec = rec;
             // cooperative copy: quarter-warp `grp` copies ray 4g+grp, lane q8 moves chunk q8 of each of its 3 lines
             __syncwarp();                                                  // previous stage's reads are done
+            recptr[lane_id] = rec;
+            __syncwarp();
 #pragma unroll
             for (int g8 = 0; g8 < 8; ++g8) {
                 const int r = 4 * g8 + grp;
-                const unsigned long long src = __shfl_sync(FULL, (unsigned long long)rec, r);
                 if ((need_mask >> r) & 1u) {
-                    const unsigned dst = stage_u32 + r * 384 + ((q8 ^ (r & 7)) << 4);
-                    const char *sp = reinterpret_cast<const char *>(src) + (q8 << 4);
+                    const char *sp = reinterpret_cast<const char *>(recptr[r]) + (q8 << 4);
+                    const unsigned dst = stage_u32 + r * CO_REC_STRIDE + (q8 << 4);
                     cp_async16(dst, sp);
                     cp_async16(dst + 128, sp + 128);
                     if (q8 < 6) cp_async16(dst + 256, sp + 256);          // chunks 22, 23 of a record are padding
@@ -552,8 +552,8 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
 #pragma unroll
             for (int k = 0; k < 11; ++k) {
                 const int qa = 2 * k, qc = 2 * k + 1;
-                const double2 ab = *reinterpret_cast<const double2 *>(my_rec + (qa >> 3) * 128 + swz[qa & 7]);
-                const double2 cd = *reinterpret_cast<const double2 *>(my_rec + (qc >> 3) * 128 + swz[qc & 7]);
+                const double2 ab = *reinterpret_cast<const double2 *>(my_rec + qa * 16);
+                const double2 cd = *reinterpret_cast<const double2 *>(my_rec + qc * 16);
                 f[k] = ab.x * wa + ab.y * wb + cd.x * wc + cd.y * wd;
             }
             masked = err;
