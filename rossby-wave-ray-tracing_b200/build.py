@@ -36,8 +36,8 @@ def _deps():
                                                                 os.path.abspath(__file__)]
 
 
-def _compile(unit, flags, log):
-    obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+def _compile(unit, flags, log, objdir=None):
+    obj = os.path.join(objdir or OBJ, unit.replace(".cu", ".o"))
     cmd = [NVCC, *ARCH, *[c for c in COMMON if not c.startswith("--use_fast_math")], *flags, "-c",
            os.path.join(CSRC, unit), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -66,5 +66,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(out: str, extra: list) -> str:
+    """A/B build of the same ABI with extra nvcc flags (e.g. -DRWRT_TMEM_KS=0) into `out`; load it with RWRT_LIB=out."""
+    objdir = out + ".obj"
+    os.makedirs(objdir, exist_ok=True)
+    log = []
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        objs = list(ex.map(lambda kv: _compile(kv[0], kv[1] + extra, log, objdir), UNITS.items()))
+    r = subprocess.run([NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(os.path.join(objdir, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:     # python build.py --variant out.so -DFOO=1 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(os.path.abspath(sys.argv[i + 1]), sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -360,6 +360,62 @@ __device__ __forceinline__ void rhs_from_merc(const Merc &m, const double *y, co
     vgo = vg;
 }
 
+// The same right-hand side in two pieces, for the pipelined integrator: rhs_position gives d lon/dt, d lat/dt and
+// (ug, vg) -- all the next stage's position needs --, rhs_wavenumber the other three components.  Operation by
+// operation identical to rhs_from_merc.
+template <bool FAST>
+__device__ __forceinline__ void rhs_position(const Merc &m, const double *y, const WaveRecip &w, double *dy, double &ugo,
+                                             double &vgo)
+{
+    double ug, vg;
+    if (FAST) {
+        const double kap = w.kap, kap2 = w.kap2, rden = w.rden;
+        ug = m.u + (((1. - kap2) * m.qy) - (2. * kap * m.qx)) * rden;
+        vg = m.v + ((2. * kap * m.qy) + ((1. - kap2) * m.qx)) * rden;
+        const double ra = 1.0 / REARTH;
+        dy[0] = ug * ra;
+        dy[1] = (vg * m.cosl) * ra;
+    } else {
+        ugvg_extent(m.u, m.v, m.qx, m.qy, y[2], y[3], ug, vg);
+        dy[0] = ug / REARTH;
+        dy[1] = (vg * m.cosl) / REARTH;
+    }
+    ugo = ug;
+    vgo = vg;
+}
+template <bool FAST>
+__device__ __forceinline__ void rhs_wavenumber(const Merc &m, const double *y, const WaveRecip &w, double *dy)
+{
+    double kx = y[2], ky = y[3], amp = y[4];
+    if (FAST) {
+        const double kap = w.kap, kap2 = w.kap2, rkk = w.rkk, rkap1 = w.rkap1, rden = w.rden;
+        double dzwn = -kx * ((m.ux + kap * m.vx) + (kap * m.qxx - m.qyx) * rkk);
+        double dmwn = -kx * ((m.uy + kap * m.vy) + (kap * m.qxy - m.qyy) * rkk);
+        double damp1 = 2.0 * (m.ux + m.vy + kap * (m.vx + m.uy)) * rkap1;
+        double damp2 = 2.0 * (kap * (m.qxx - m.qyy) + (kap2 - 1.0) * m.qxy) * rden;
+        double damp3 = -2.0 * m.sinl * m.v;
+        double damp = damp1 + damp2 + damp3;
+        const double ra = 1.0 / REARTH;
+        dy[2] = dzwn * ra;
+        dy[3] = dmwn * ra;
+        dy[4] = (damp * amp) * ra;
+        return;
+    }
+    double kap = ky / kx;
+    double kap2 = kap * kap;
+    double kap1 = 1 + kap * kap;
+    double kk = kx * kx * kap1;
+    double dzwn = -kx * ((m.ux + kap * m.vx) + (kap * m.qxx - m.qyx) / kk);
+    double dmwn = -kx * ((m.uy + kap * m.vy) + (kap * m.qxy - m.qyy) / kk);
+    double damp1 = 2.0 * (m.ux + m.vy + kap * (m.vx + m.uy)) / kap1;
+    double damp2 = 2.0 * (kap * (m.qxx - m.qyy) + (kap2 - 1.0) * m.qxy) / (kk * kap1);
+    double damp3 = -2.0 * m.sinl * m.v;
+    double damp = damp1 + damp2 + damp3;
+    dy[2] = dzwn / REARTH;
+    dy[3] = dmwn / REARTH;
+    dy[4] = (damp * amp) / REARTH;
+}
+
 // ugo / vgo: the group velocity at y (m/s), which is also what the reference stores at output times
 // (wr.py:856-865 re-samples at the same point with the same formula).  masked is set when the
 // |lat| / |l| mask fired (then ugo / vgo are not computed here).

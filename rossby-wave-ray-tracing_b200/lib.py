@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librwrt.so")
+LIB_PATH = os.environ.get("RWRT_LIB") or os.path.join(HERE, "librwrt.so")   # RWRT_LIB: A/B builds of the same ABI
 
 MODE_FAST = 0
 MODE_STRICT = 1
