@@ -53,6 +53,16 @@ def workload(name, rank=0):
         slon, slat = synthetic.all_gridpoint_sources(nlon, nlat, 88.0)
         slon, slat = slon[rank % stride::stride], slat[rank % stride::stride]
         zwn, days = np.arange(1.0, 7.0), 30.0
+    elif name in ("c5", "c5-small"):
+        # BASELINE configs[4]: 0.25 deg Clim background, 1440 x 386 sources (|lat| <= 48.125 deg) x k=1..6 x 3 roots
+        # = 10.0 M ray slots, 60 days.  One GPU integrates one eighth of the sources (every 8th, offset by rank):
+        # 1.25 M slots, 50 GB of trajectories -- the per-GPU share of the 8-GPU run.
+        nlon, nlat = 1440, 721
+        u, v = synthetic.clim(nlon, nlat)
+        slon, slat = synthetic.all_gridpoint_sources(nlon, nlat, 48.125)
+        stride = 8 if name == "c5" else 128
+        slon, slat = slon[rank % stride::stride], slat[rank % stride::stride]
+        zwn, days = np.arange(1.0, 7.0), 60.0
     else:
         raise SystemExit(f"unknown workload {name}")
     lon, lat = synthetic.grid_coords(nlon, nlat)
@@ -307,7 +317,7 @@ def run_ours(a):
     line = {"metric": "accepted RK45 ray-steps/s (fp64)", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{a.workload}: Clim 1deg background, {nsource} sources x k=1..{nzwn} x 3 roots = {N} "
+            "config": {"workload": f"{a.workload}: Clim {360.0 / nlon:g}deg background, {nsource} sources x k=1..{nzwn} x 3 roots = {N} "
                                    f"ray slots per GPU, {wl['days']:.0f} d, tstep 2 h, nt={nt}, rtol=atol=1e-6",
                        "mode": "strict" if a.strict else "fast", "accepted_steps_per_step_per_gpu": steps_per_launch,
                        "l2": "flushed between timed iterations (256 MB write); outputs (23 GB) exceed L2 anyway",

@@ -140,8 +140,10 @@ __device__ __forceinline__ void sincos_halfpi(double x, double &sn, double &cs)
     pc = fma(z, pc, cSinCos[6]);
     const double sr = fma(r * z, ps, r);                           // sin(r)
     const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));          // cos(r)
-    sn = (q == 0.0) ? sr : ((q > 0.0) ? cr : -cr);
-    cs = (q == 0.0) ? cr : ((q > 0.0) ? -sr : sr);
+    // quadrant fix-up without selects: q is -1, 0 or 1, so every product below is exact (x0, x1, x-1)
+    const double nq2 = fma(-q, q, 1.0);                            // 1 - q^2: 1 in the centre, 0 in the folded quadrants
+    sn = fma(q, cr, nq2 * sr);
+    cs = fma(-q, sr, nq2 * cr);
 }
 
 // FAST-build sine of a small angle (the speed cut-off's sin(dlat/2), sin(dlon/2)): the fdlibm kernel polynomial
