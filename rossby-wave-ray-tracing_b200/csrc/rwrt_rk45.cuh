@@ -410,8 +410,80 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
 // ---------------------------------------------------------------------------------------------
 constexpr int CO_REC_STRIDE = 368;   // 23 x 16 B per staged ray: chunk q of ray r sits in bank group (q - r) mod 8,
                                      // so a quarter-warp's LDS.128 / LDGSTS never conflict -- no swizzle arithmetic
-constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE + 256;                   // per warp: records + 32 record pointers
+constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE + 256;                   // per warp: records + fetch list
+
+// Stage vectors K2..K6 (25 doubles per ray) live in TENSOR MEMORY: lane = thread, 10 x 32-bit columns per
+// stage vector, 64 columns per block.  That takes 6.25 KB per warp out of shared memory, which was what
+// capped residency at 12 warps per SM; with TMEM the kernel runs 4 blocks = 16 warps per SM (and fits 128
+// registers).  No tensor-core instruction is involved -- tcgen05.ld / .st with the 32x32b shape give every
+// thread a private 32-bit x ncol scratch row.  RWRT_TMEM_KS=1 selects it; measured slower than the shared-memory layout at 12 warps, so off by default.
+#ifndef RWRT_TMEM_KS
+#define RWRT_TMEM_KS 0
+#endif
+constexpr int CO_TMEM_COLS = 64;     // power of two >= 50
+#ifndef RWRT_CO_BLOCKS
+#define RWRT_CO_BLOCKS 4
+#endif
+#if RWRT_TMEM_KS
+constexpr int CO_BLOCKS_PER_SM = RWRT_CO_BLOCKS;
+constexpr int CO_SMEM_BYTES = (RK_THREADS / 32) * CO_STAGE_BYTES + 16;
+#else
+constexpr int CO_BLOCKS_PER_SM = 3;
 constexpr int CO_SMEM_BYTES = (RK_THREADS / 32) * CO_STAGE_BYTES + 5 * 5 * RK_THREADS * (int)sizeof(double);
+#endif
+
+// one stage vector (5 doubles = 10 columns) TMEM -> registers; the values may be used after tm_wait_ld(v)
+__device__ __forceinline__ void tm_ld5(unsigned taddr, unsigned (&v)[10])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(v[8]), "=r"(v[9]) : "r"(taddr + 8));
+}
+// the "+r" operands tie the loaded registers to the wait, so that no use of them is scheduled before it
+__device__ __forceinline__ void tm_wait_ld(unsigned (&v)[10])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]));
+}
+__device__ __forceinline__ double tm_val(const unsigned (&v)[10], int c) { return __hiloint2double((int)v[2 * c + 1], (int)v[2 * c]); }
+__device__ __forceinline__ void tm_st5(unsigned taddr, const double *k)
+{
+    unsigned v[10];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        v[2 * c] = (unsigned)__double2loint(k[c]);
+        v[2 * c + 1] = (unsigned)__double2hiint(k[c]);
+    }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};\n" ::"r"(taddr + 8), "r"(v[8]), "r"(v[9]) : "memory");
+}
+__device__ __forceinline__ void tm_wait_st()
+{
+#ifndef RWRT_TM_NOWAITST
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+#endif
+}
+
+// sum_{j<S} K_j[c] * coef[j] in j order (K_1 = k1 in registers, K_2.. from tensor memory); S = number of terms
+template <int S>
+__device__ __forceinline__ void tm_combo(unsigned tk, const double *k1, const double *coef, double *a)
+{
+    unsigned v[S > 1 ? S - 1 : 1][10];
+#pragma unroll
+    for (int j = 0; j < S - 1; ++j) tm_ld5(tk + 10 * j, v[j]);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) a[c] = k1[c] * coef[0];
+#pragma unroll
+    for (int j = 0; j < S - 1; ++j) {
+        tm_wait_ld(v[j]);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) a[c] = a[c] + tm_val(v[j], c) * coef[j + 1];
+    }
+}
 
 // The cell table (25 MB at 1 degree) must stay in L2 while 23 GB of trajectories stream through it: 13 % of the
 // record sectors missed L2 under the default policy, and since a warp waits for ~120 sectors per stage nearly every
@@ -438,16 +510,33 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src, u
 #endif
 }
 
-__global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p)
+__global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_coop(RunParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
     const int lane_id = tid & 31, warp_id = tid >> 5;
     unsigned char *stage = smem_raw + warp_id * CO_STAGE_BYTES;            // this warp's 32 x 384 B
-    double *ks = reinterpret_cast<double *>(smem_raw + (RK_THREADS / 32) * CO_STAGE_BYTES);
     const unsigned stage_u32 = (unsigned)__cvta_generic_to_shared(stage);
+#if RWRT_TMEM_KS
+    // tensor-memory scratch for K2..K6: warp 0 allocates 64 columns, every warp addresses its own 32 lanes
+    unsigned *tm_slot = reinterpret_cast<unsigned *>(smem_raw + (RK_THREADS / 32) * CO_STAGE_BYTES);
+    if (warp_id == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(tm_slot)),
+                     "n"(CO_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tm_base = *tm_slot;
+    const unsigned tk = tm_base + ((unsigned)(warp_id * 32) << 16);       // + 10 * (s - 1): K_{s+1}, s = 1..5
+#else
+    double *ks = reinterpret_cast<double *>(smem_raw + (RK_THREADS / 32) * CO_STAGE_BYTES);
 #define KS(s, c) ks[(((s) - 1) * 5 + (c)) * RK_THREADS + tid]            /* K2..K6 <-> s = 1..5 */
+#endif
     Lane L;
     L.slot = -1;
     double k1[5] = {0, 0, 0, 0, 0};
@@ -571,6 +660,38 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             const double lat = ys[1];
             const double wa = (1 - sx) * sy, wb = sx * sy, wc = (1 - sx) * (1 - sy), wd = sx * (1 - sy);
             const bool err = (fabs(lat) >= HALFPI) || (fabs(ys[3]) >= 100.0);   // wr.py:508-510
+            // the part of the NEXT stage's input that is already known: sum_{j<=s} K_j c_{s+1,j} (j order, rkf45.py:310);
+            // this stage's own K_{s+1} c_{s+1,s+1} is added last, below.  Read here, the stage vectors arrive from
+            // shared memory under the copy wait instead of on the critical path behind the right-hand side.
+            double part[5];
+#if RWRT_TMEM_KS
+            __syncwarp();
+            if (s > 1) tm_wait_st();                                       // K_s of the previous stage has landed
+            switch (s) {
+                case 1: tm_combo<1>(tk, k1, cC[2], part); break;
+                case 2: tm_combo<2>(tk, k1, cC[3], part); break;
+                case 3: tm_combo<3>(tk, k1, cC[4], part); break;
+                case 4: tm_combo<4>(tk, k1, cC[5], part); break;
+                case 5: tm_combo<5>(tk, k1, cC[6], part); break;
+                default:
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) part[c] = 0.0;
+                    break;
+            }
+#else
+#define RWRT_PART(c) \
+    switch (s) { \
+        case 1: part[c] = k1[c] * cC[2][0]; break; \
+        case 2: part[c] = k1[c] * cC[3][0] + KS(1, c) * cC[3][1]; break; \
+        case 3: part[c] = k1[c] * cC[4][0] + KS(1, c) * cC[4][1] + KS(2, c) * cC[4][2]; break; \
+        case 4: part[c] = k1[c] * cC[5][0] + KS(1, c) * cC[5][1] + KS(2, c) * cC[5][2] + KS(3, c) * cC[5][3]; break; \
+        case 5: part[c] = k1[c] * cC[6][0] + KS(1, c) * cC[6][1] + KS(2, c) * cC[6][2] + KS(3, c) * cC[6][3] + KS(4, c) * cC[6][4]; break; \
+        default: part[c] = 0.0; break; \
+    }
+            RWRT_PART(0) RWRT_PART(1) RWRT_PART(2) RWRT_PART(3) RWRT_PART(4)
+#undef RWRT_PART
+#endif
+            const double clast = cC[s < 6 ? s + 1 : 6][s < 6 ? s : 5];      // coefficient of this stage's K_{s+1} in stage s+1's input
             const Trig tg = trig_of_lat<RWRT_FAST>(inr ? lat : 0.0);
             // wr.py:508-510 sets l := NaN under the mask and computes on: every derivative and ug, vg come out NaN
             // (they all depend on l / k).  Same here, by poisoning l -- no branch.
@@ -581,6 +702,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             // free to sink that arithmetic below it, which exposes the whole copy latency)
             double wa_ = wa, wd_ = wd, tcp = tg.cp, ttl = tg.tl, wkap = RWRT_FAST ? wr.kap : 0.0, wrden = RWRT_FAST ? wr.rden : 0.0;
             asm volatile("" : "+d"(wa_), "+d"(wd_), "+d"(tcp), "+d"(ttl), "+d"(wkap), "+d"(wrden));
+            asm volatile("" : "+d"(part[0]), "+d"(part[1]), "+d"(part[2]), "+d"(part[3]), "+d"(part[4]));
             // ... and the wait sits in a basic block of its own (always taken: nt >= 2 here), or ptxas hoists the
             // DEPBAR to the top of the block to start the record loads early
             if (p.nt > 1) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -608,14 +730,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             double yn[5];
             if (s < 6) {
                 // next stage's position: y + (sum_{j<=s} K_j c) h with K_{s+1} = kn still in registers
-#define RWRT_NEXT(c) \
-    switch (s) { \
-        case 1: yn[c] = L.y[c] + (k1[c] * cC[2][0] + kn[c] * cC[2][1]) * h; break; \
-        case 2: yn[c] = L.y[c] + (k1[c] * cC[3][0] + KS(1, c) * cC[3][1] + kn[c] * cC[3][2]) * h; break; \
-        case 3: yn[c] = L.y[c] + (k1[c] * cC[4][0] + KS(1, c) * cC[4][1] + KS(2, c) * cC[4][2] + kn[c] * cC[4][3]) * h; break; \
-        case 4: yn[c] = L.y[c] + (k1[c] * cC[5][0] + KS(1, c) * cC[5][1] + KS(2, c) * cC[5][2] + KS(3, c) * cC[5][3] + kn[c] * cC[5][4]) * h; break; \
-        default: yn[c] = L.y[c] + (k1[c] * cC[6][0] + KS(1, c) * cC[6][1] + KS(2, c) * cC[6][2] + KS(3, c) * cC[6][3] + KS(4, c) * cC[6][4] + kn[c] * cC[6][5]) * h; break; \
-    }
+#define RWRT_NEXT(c) yn[c] = L.y[c] + (part[c] + kn[c] * clast) * h;
                 RWRT_NEXT(0)
                 RWRT_NEXT(1)
                 __syncwarp();                                              // every lane has read its record of stage s
@@ -626,8 +741,13 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             }
             rhs_wavenumber<RWRT_FAST>(m, yp, wr, kn);                     // kn[2], kn[3], kn[4]
             if (s < 6) {
+#if RWRT_TMEM_KS
+                __syncwarp();
+                tm_st5(tk + 10 * (s - 1), kn);
+#else
 #pragma unroll
                 for (int c = 0; c < 5; ++c) KS(s, c) = kn[c];
+#endif
                 RWRT_NEXT(2)
                 RWRT_NEXT(3)
                 RWRT_NEXT(4)
@@ -637,15 +757,30 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
         }
 #undef RWRT_NEXT
 #undef RWRT_FETCH
+        // now ys = y_new and kn = f(y_new) (rkf45.py:317-319); error estimate sum_s K_s E_s (rkf45.py:442-446)
+        double ee[5];
+#if RWRT_TMEM_KS
+        {
+            const double cE[6] = {E1, E2, E3, E4, E5, E6};
+            __syncwarp();
+            tm_wait_st();
+            tm_combo<6>(tk, k1, cE, ee);                                   // warp-wide (tcgen05.ld is .sync.aligned)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) ee[c] = ee[c] + kn[c] * E7;
+        }
         if (!active) continue;
+#else
+        if (!active) continue;
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+            ee[c] = k1[c] * E1 + KS(1, c) * E2 + KS(2, c) * E3 + KS(3, c) * E4 + KS(4, c) * E5 + KS(5, c) * E6 + kn[c] * E7;
+#endif
         ++L.att;
-        // now ys = y_new and kn = f(y_new) (rkf45.py:317-319)
         double r[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {  // rkf45.py:442-446
             double scale = p.atol + np_maximum(fabs(L.y[c]), fabs(ys[c])) * p.rtol;
-            double e = k1[c] * E1 + KS(1, c) * E2 + KS(2, c) * E3 + KS(3, c) * E4 + KS(4, c) * E5 + KS(5, c) * E6 +
-                       kn[c] * E7;
+            const double e = ee[c];
             r[c] = RWRT_FAST ? (h * e) * rcp_fast(scale) : (h * e) / scale;   // scale >= atol > 0, never denormal
         }
         double err = rms5(r[0], r[1], r[2], r[3], r[4]);
@@ -743,7 +878,15 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk45_integrate_coop(RunParams p
             L.it = 1;
         }
     }
+#if RWRT_TMEM_KS
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp_id == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm_base), "n"(CO_TMEM_COLS) : "memory");
+#else
 #undef KS
+#endif
     for (int o = 16; o > 0; o >>= 1) my_total += __shfl_down_sync(FULL, my_total, o);
     if (lane_id == 0 && my_total) atomicAdd(p.total_accepted, (unsigned long long)my_total);
 }

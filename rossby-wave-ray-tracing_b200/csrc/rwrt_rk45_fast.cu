@@ -34,6 +34,11 @@ int occupancy_rk45_fast(bool coop)
     if (coop) {
         cudaFuncSetAttribute(fast::rk45_integrate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::CO_SMEM_BYTES);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast::rk45_integrate_coop, fast::RK_THREADS, fast::CO_SMEM_BYTES);
+#if RWRT_TMEM_KS
+        // the occupancy calculator answers 1 for a kernel that allocates tensor memory (it cannot know how many
+        // columns tcgen05.alloc will ask for); this build takes 64 of the 512 columns per block
+        if (nb < fast::CO_BLOCKS_PER_SM) nb = fast::CO_BLOCKS_PER_SM;
+#endif
         return nb;
     }
     cudaFuncSetAttribute(fast::rk45_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RK_SMEM_BYTES);

@@ -34,6 +34,11 @@ int occupancy_rk45_strict(bool coop)
     if (coop) {
         cudaFuncSetAttribute(strict::rk45_integrate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::CO_SMEM_BYTES);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, strict::rk45_integrate_coop, strict::RK_THREADS, strict::CO_SMEM_BYTES);
+#if RWRT_TMEM_KS
+        // the occupancy calculator answers 1 for a kernel that allocates tensor memory (it cannot know how many
+        // columns tcgen05.alloc will ask for); this build takes 64 of the 512 columns per block
+        if (nb < strict::CO_BLOCKS_PER_SM) nb = strict::CO_BLOCKS_PER_SM;
+#endif
         return nb;
     }
     cudaFuncSetAttribute(strict::rk45_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::RK_SMEM_BYTES);
