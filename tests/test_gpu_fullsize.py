@@ -1,0 +1,134 @@
+"""Full-size GPU checks (BASELINE.json configs[1]: 63 720 sources x k=1..6 x 3 roots = 1 146 960 ray slots,
+30 days, 23.2 GB of trajectories on the device) through the C ABI with device buffers.  The oracle cannot
+run this size in seconds, so the run is checked through size-independent properties of the reference's
+algorithm, plus bit-exact agreement of a random sample of sources with small runs of the same engine
+(which the other tests pin against the oracle and the reference fixtures):
+
+  * a ray's bits do not depend on its batch (SURVEY.md probe9)              -> sample == small runs, bit for bit
+  * NaN is absorbing (wr.py:838-855: a terminated ray stays NaN)            -> NaN mask monotone in time
+  * NaN-root slots never move                      -> lon/lat/k rows constant, rest NaN
+  * |lat| < pi/2 wherever a ray is alive (wr.py:838-843)
+  * accepted-step bookkeeping: sum(accepted) == total, accepted == 0 on NaN-root slots, >= alive rows - 1 on live
+  * idempotence and time-window invariance (checksum of the raw bits of all seven planes)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import rwrt_b200  # noqa: F401
+from rwrt_b200 import lib, synthetic
+
+pytestmark = pytest.mark.gpu
+
+TSTEP, DAYS = 7200.0, 30.0
+
+
+def _setup(nlon, nlat, slon_deg, slat_deg, zwn):
+    import torch
+    L = lib.load()
+    lib.require_gpu()
+    dev = torch.device("cuda", 0)
+    u, v = synthetic.clim(nlon, nlat)
+    lon, lat = synthetic.grid_coords(nlon, nlat)
+    h = lib.vp()
+    lib.check(L.rwrt_create(0, nlon, nlat, 1, 1, C.byref(h)), "rwrt_create")
+    d = {k: torch.from_numpy(np.ascontiguousarray(x)).to(dev) for k, x in
+         dict(u=u, v=v, lon=lon, lat=lat, cl=np.cos(lat), sl=np.sin(lat), slon=np.radians(slon_deg),
+              slat=np.radians(slat_deg), zwn=zwn).items()}
+    sp = lib.stream_ptr()
+    lib.check(L.rwrt_bs_ready(h, lib.ptr(d["u"]), lib.ptr(d["v"]), lib.ptr(d["lon"]), lib.ptr(d["lat"]),
+                              lib.ptr(d["cl"]), lib.ptr(d["sl"]), None, None, sp), "rwrt_bs_ready")
+    return L, h, d, dev
+
+
+def _run(L, h, d, dev, nsource, nzwn, flags=lib.MODE_FAST):
+    import torch
+    nt = int(DAYS * 86400.0 / TSTEP) + 1
+    N = 3 * nsource * nzwn
+    out = torch.empty((7, nt, N), dtype=torch.float64, device=dev)
+    acc = torch.zeros(N, dtype=torch.int64, device=dev)
+    status = torch.zeros(N, dtype=torch.int8, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    sp = lib.stream_ptr()
+    lib.check(L.rwrt_ray_init(h, nsource, lib.ptr(d["slon"]), lib.ptr(d["slat"]), None, nzwn, lib.ptr(d["zwn"]), 0.0, nt,
+                              lib.ptr(out), sp), "rwrt_ray_init")
+    lib.check(L.rwrt_ray_run_rk45(h, nsource, None, nzwn, nt, TSTEP, DAYS * 86400.0, 1e-6, 1e-6, 1e-3, 0.1, flags,
+                                  lib.ptr(out), lib.ptr(acc), None, lib.ptr(status), lib.ptr(total), sp), "rwrt_ray_run_rk45")
+    torch.cuda.synchronize()
+    return out, acc, status, int(total.item()), nt, N
+
+
+def _checksum(out):
+    # sum of the raw 64-bit patterns (wraps modulo 2^64): equal bits <=> equal checksum, NaNs included
+    return int(out.view(-1).view(dtype=__import__("torch").int64).sum().item())
+
+
+def test_c2_full_size_properties(monkeypatch):
+    import torch
+    nlon, nlat = 360, 181
+    slon_deg, slat_deg = synthetic.all_gridpoint_sources(nlon, nlat, 88.0)
+    zwn = np.arange(1.0, 7.0)
+    ns, nz = len(slon_deg), len(zwn)
+    assert 3 * ns * nz == 1146960
+    L, h, d, dev = _setup(nlon, nlat, slon_deg, slat_deg, zwn)
+    try:
+        out, acc, status, total, nt, N = _run(L, h, d, dev, ns, nz)
+        assert int(acc.sum().item()) == total and total > 2.0e8
+        nan_l = torch.isnan(out[3])                                        # (nt, N): meridional wavenumber plane
+        static = nan_l[0]                                                  # NaN root at t = 0
+        # NaN is absorbing
+        assert bool((nan_l[1:] | ~nan_l[:-1]).all()), "a ray came back from NaN"
+        # NaN-root slots: lon, lat, k constant; l, A, ug, vg NaN; zero steps; status NO_ROOT
+        for pl in range(3):
+            col = out[pl][:, static]
+            assert bool(((col == col[0:1]) | (torch.isnan(col) & torch.isnan(col[0:1]))).all()), pl
+        for pl in (3, 5, 6):
+            assert bool(torch.isnan(out[pl][1:, static]).all()), pl
+        assert int(acc[static].abs().sum().item()) == 0
+        assert bool((status[static] == lib.RAY_NO_ROOT).all()) and bool((status[~static] != lib.RAY_NO_ROOT).all())
+        # alive rows: every plane finite, |lat| < pi/2
+        alive = ~nan_l
+        alive[:, static] = False
+        for pl in range(5):
+            assert bool(torch.isfinite(out[pl][alive]).all()), pl
+        assert float(out[1][alive].abs().max().item()) < np.pi / 2
+        # dead rows of live slots: all seven planes NaN
+        dead = nan_l.clone()
+        dead[:, static] = False
+        for pl in range(7):
+            assert bool(torch.isnan(out[pl][dead]).all()), pl
+        # bookkeeping: a live ray that produced r rows took at least r - 1 accepted steps; survivors are ALIVE
+        rows_alive = alive.sum(dim=0)
+        live = ~static
+        assert bool((acc[live] >= rows_alive[live] - 1).all())
+        assert bool((status[live & (rows_alive == nt)] == lib.RAY_ALIVE).all())
+        assert bool((status[live & (rows_alive < nt)] >= lib.RAY_POLE).all())
+        del nan_l, alive, dead
+        # sample of sources re-run alone in small batches: identical bits (fast build)
+        rng = np.random.default_rng(7)
+        idx = np.sort(rng.choice(ns, size=384, replace=False))
+        L2, h2, d2, _ = _setup(nlon, nlat, slon_deg[idx], slat_deg[idx], zwn)
+        try:
+            o2, a2, s2, t2, _, N2 = _run(L2, h2, d2, dev, len(idx), nz)
+        finally:
+            L2.rwrt_destroy(h2)
+        big = out.view(7, nt, 3, ns, nz)[:, :, :, torch.from_numpy(idx).to(dev), :]
+        small = o2.view(7, nt, 3, len(idx), nz)
+        same = (big == small) | (torch.isnan(big) & torch.isnan(small))
+        assert bool(same.all()), "a ray's bits depend on its batch"
+        assert torch.equal(acc.view(3, ns, nz)[:, torch.from_numpy(idx).to(dev), :], a2.view(3, len(idx), nz))
+        del big, small, same, o2
+        # idempotence and time-window invariance on the whole 23 GB
+        ck, acc0 = _checksum(out), acc.clone()
+        del out
+        torch.cuda.empty_cache()
+        out, acc, status, total2, _, _ = _run(L, h, d, dev, ns, nz)
+        assert _checksum(out) == ck and total2 == total and torch.equal(acc, acc0)
+        del out
+        torch.cuda.empty_cache()
+        monkeypatch.setenv("RWRT_WINDOWS", "5")
+        out, acc, status, total3, _, _ = _run(L, h, d, dev, ns, nz)
+        assert _checksum(out) == ck and total3 == total and torch.equal(acc, acc0)
+    finally:
+        L.rwrt_destroy(h)
