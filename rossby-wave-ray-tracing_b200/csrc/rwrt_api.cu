@@ -510,6 +510,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     else launch_rk45_setup_fast(p, prepare_blocks, fill_blocks, s, h->aux);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_join, h->aux));
+    CU(cudaStreamWaitEvent(s, h->ev_join, 0));     // join: the pre-fill (all rows >= 1) precedes the integrator's writes
     if (!coop || nwin < 1) nwin = 1;               // only the cooperative kernel can park rays at a window end
     if (nwin > nt - 1) nwin = nt - 1;
     int launches = 0;
@@ -521,7 +522,6 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         else launch_rk45_window_fast(p, integrate_blocks, s);
         CU(cudaGetLastError());
         ++launches;
-        if (w == 0) CU(cudaStreamWaitEvent(s, h->ev_join, 0));  // join: rows of NaN-root slots are complete too
         if (hook) {
             int rc = hook(hook_ctx, p.it_begin, p.it_end, s);
             if (rc) return rc;

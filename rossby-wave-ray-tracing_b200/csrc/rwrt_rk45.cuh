@@ -120,8 +120,13 @@ __global__ void __launch_bounds__(128) rk45_prepare(RunParams p)
     reinterpret_cast<int *>(st + 15)[1] = 0;  // attempts so far; bit 31 set = ray finished
 }
 
-// NaN-root slots: rlon, rlat, rzwn keep their t=0 value at every output
-// time, the other four planes are NaN; their step count is zero.
+// Pre-fill of the output rows 1..nt-1, whole rows, fully coalesced (a streaming write at HBM speed):
+//   * NaN-root slots: rlon, rlat, rzwn keep their t=0 value at every output time, the
+//     other four planes are NaN; their step count is zero;
+//   * live slots: NaN in all seven planes -- the integrator then overwrites the rows a ray is alive for, and a
+//     ray that dies (wr.py:838-855) leaves its tail as it is instead of writing NaN rows one by one.
+// Writing only the static slots (v1-v11) cost twice the time for a third of the bytes: static and live slots
+// interleave below sector granularity, so DRAM did a read-modify-write for most sectors.
 __global__ void __launch_bounds__(256) fill_static_slots(RunParams p)
 {
     long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,24 +135,25 @@ __global__ void __launch_bounds__(256) fill_static_slots(RunParams p)
     double v0 = p.out[0 * pl + slot], v1 = p.out[1 * pl + slot], v2 = p.out[2 * pl + slot], v3 = p.out[3 * pl + slot],
            v4 = p.out[4 * pl + slot];
     double s = v0 + v1 + v2 + v3 + v4;
-    if (s == s) return;  // live slot: written by the integrator
     const double n = qnan();
+    const bool live = (s == s);  // finite t=0 state: the integrator owns this slot
+    if (live) v0 = v1 = v2 = v3 = v4 = n;
     // this block's share of the output rows (gridDim.y chunks); consecutive threads write consecutive slots
     int per = (p.nt - 1 + gridDim.y - 1) / gridDim.y;
     int it0 = 1 + blockIdx.y * per, it1 = min(p.nt, it0 + per);
     for (int it = it0; it < it1; ++it) {
         size_t o = (size_t)it * p.N + slot;
-        // the t=0 values stay (NaN root stays NaN, a NaN position stays NaN): the reference never advances such a slot
-        p.out[0 * pl + o] = v0;
-        p.out[1 * pl + o] = v1;
-        p.out[2 * pl + o] = v2;
-        p.out[3 * pl + o] = v3;
-        p.out[4 * pl + o] = v4;
-        // ug, vg at outputs: fresh sample + extent form (wr.py:856-865); NaN because l or the state is NaN
-        p.out[5 * pl + o] = n;
-        p.out[6 * pl + o] = n;
+        // static slot: the t=0 values stay (NaN root stays NaN, a NaN position stays NaN): the reference never
+        // advances it; ug, vg at outputs: fresh sample + extent form (wr.py:856-865) -- NaN because l or the state is NaN
+        __stcs(p.out + 0 * pl + o, v0);
+        __stcs(p.out + 1 * pl + o, v1);
+        __stcs(p.out + 2 * pl + o, v2);
+        __stcs(p.out + 3 * pl + o, v3);
+        __stcs(p.out + 4 * pl + o, v4);
+        __stcs(p.out + 5 * pl + o, n);
+        __stcs(p.out + 6 * pl + o, n);
     }
-    if (blockIdx.y == 0) {
+    if (blockIdx.y == 0 && !live) {
         if (p.accepted) p.accepted[slot] = 0;
         if (p.attempts) p.attempts[slot] = 0;
         if (p.status) p.status[slot] = 0;
@@ -365,10 +371,7 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
                 code = 3;
             }
         }
-        if (dead) {
-            double n = qnan();
-            for (int it = L.it; it < p.nt; ++it) write_row(p, L.slot, it, n, n, n, n, n, n, n);
-        } else {
+        if (!dead) {  // a dead ray's remaining rows are NaN already (pre-filled)
             // wr.py:856-865: ug, vg at the output point = what the last stage evaluated at y_new
             if (masked) {
                 double2 gv = output_ugvg_slow(p.g, fb, L.y[0], L.y[1], L.y[2], L.y[3]);
@@ -828,10 +831,7 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                 code = 3;
             }
         }
-        if (dead) {
-            double n = qnan();
-            for (int it = L.it; it < p.nt; ++it) write_row(p, L.slot, it, n, n, n, n, n, n, n);
-        } else {
+        if (!dead) {  // a dead ray's remaining rows are NaN already (pre-filled)
             // wr.py:856-865: ug, vg at the output point = what the last stage evaluated at y_new
             if (masked) {
                 double2 gv = output_ugvg_slow(p.g, fb, L.y[0], L.y[1], L.y[2], L.y[3]);

@@ -10,7 +10,7 @@ void launch_rk45_setup_strict(const RunParams &p, int prepare_blocks, int fill_b
     if (p.nlive > 0) strict::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
     // The constant rows of NaN-root slots touch no slot the integrator writes: low-priority side stream.
     if (p.N > 0 && p.nt > 1)
-        strict::fill_static_slots<<<dim3(fill_blocks, p.nt - 1 < 8 ? p.nt - 1 : 8), 256, 0, aux>>>(p);
+        strict::fill_static_slots<<<dim3(fill_blocks, p.nt - 1 < 24 ? p.nt - 1 : 24), 256, 0, aux>>>(p);
 }
 
 // One time window [p.it_begin, p.it_end) of output rows for every live ray (the point-major kernel has no
