@@ -86,7 +86,7 @@ struct rwrt_ctx {
         g.dlat = dlat;
         g.rdlon = 1.0 / dlon;
         g.rdlat = 1.0 / dlat;
-        g.fcell = have_cells ? (const double *)fcell.p : nullptr;
+        g.fcell = have_cells ? (const double *)(fcell.p ? fcell.p : fpk.p) : nullptr;   // non-null selects the cooperative kernel
         g.cell_member_stride = (size_t)nlon_f * nlat * NCELL;
         return g;
     }
@@ -311,6 +311,13 @@ static int build_cell_table(rwrt_handle h, cudaStream_t s)
     size_t bytes = (size_t)h->nmember * h->nlon_f * h->nlat * NCELL * sizeof(double);
     size_t limit_mb = 100;
     if (const char *e = getenv("RWRT_CELL_LIMIT_MB")) limit_mb = (size_t)atol(e);
+    if (!coop_needs_cell_table_fast() && !coop_needs_cell_table_strict()) {
+        // default build: the cooperative kernel gathers from the packed point table itself, no copy is needed;
+        // RWRT_CELL_LIMIT_MB=0 still selects the per-lane kernel (cross-check of the two gather implementations)
+        h->fcell.release();
+        h->have_cells = (limit_mb != 0);
+        return RWRT_OK;
+    }
     if (bytes > limit_mb * 1024 * 1024) return RWRT_OK;
     if (h->fcell.reserve(bytes)) return RWRT_OK;  // not fatal: fall back to the point-major kernel
     Grid g = h->grid();

@@ -411,9 +411,32 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
 // record back with conflict-free LDS.128.  Arithmetic and operation order are unchanged.
 // Shared memory per warp: 11.75 KB stage + 6.25 KB for K2..K6 -> 3 blocks of 128 threads per SM.
 // ---------------------------------------------------------------------------------------------
+// RWRT_POINT_FETCH=1: the warp gathers the four corner points of a ray's cell straight from the packed POINT table
+// (4 x 96 B; the two latitude neighbours are contiguous) instead of one 384-byte record of a cell-major copy.
+// Same number of 16-byte copies per ray, but the table is 4x smaller (6.3 MB at 1 deg, 100 MB at 0.25 deg, 6.3 GB
+// for a 1000-member ensemble) -- so every configuration runs on this kernel and no cell table is built.
+#ifndef RWRT_POINT_FETCH
+#define RWRT_POINT_FETCH 1
+#endif
+#ifndef RWRT_BENIGN_POS
+#define RWRT_BENIGN_POS(c) 0.0   /* (lon, lat) of the state idle lanes run along on */
+#endif
+#if RWRT_POINT_FETCH
+constexpr int CO_REC_STRIDE = 400;   // 25 x 16 B per staged ray (4 points x 96 B + 16 B holding the fetch-list entry):
+                                     // an odd number of 16-byte chunks, so a quarter-warp's LDS.128 / LDGSTS never conflict
+#ifdef RWRT_DBG_LIST
+constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE + 256;
+constexpr int CO_LIST_OFS = 32 * CO_REC_STRIDE, CO_LIST_STRIDE = 8;
+#else
+constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE;                         // per warp; 4 warps + K2..K6 = 76 800 B = 3 blocks / SM exactly
+constexpr int CO_LIST_OFS = 384, CO_LIST_STRIDE = CO_REC_STRIDE;           // fetch-list entry j sits in the pad of row j
+#endif
+#else
 constexpr int CO_REC_STRIDE = 368;   // 23 x 16 B per staged ray: chunk q of ray r sits in bank group (q - r) mod 8,
                                      // so a quarter-warp's LDS.128 / LDGSTS never conflict -- no swizzle arithmetic
 constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE + 256;                   // per warp: records + fetch list
+constexpr int CO_LIST_OFS = 32 * CO_REC_STRIDE, CO_LIST_STRIDE = 8;
+#endif
 
 // Stage vectors K2..K6 (25 doubles per ray) live in TENSOR MEMORY: lane = thread, 10 x 32-bit columns per
 // stage vector, 64 columns per block.  That takes 6.25 KB per warp out of shared memory, which was what
@@ -544,10 +567,12 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     L.slot = -1;
     double k1[5] = {0, 0, 0, 0, 0};
 #pragma unroll
-    for (int c = 0; c < 5; ++c) L.y[c] = (c < 2) ? 0.0 : 1.0;              // benign state for idle lanes
+    for (int c = 0; c < 5; ++c) L.y[c] = (c < 2) ? RWRT_BENIGN_POS(c) : 1.0;              // benign state for idle lanes
     L.h_abs = 1.0;
     L.t = 0.0;
+#if !RWRT_POINT_FETCH
     const double *fcb = p.g.fcell;
+#endif
     const double *fb = p.g.fpk;
     bool queue_empty = false;
     long long my_total = 0;
@@ -559,7 +584,13 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     const double shc = sin(0.5 * p.cut), sin2_half_cut = (p.cut >= PI) ? 2.0 : shc * shc;  // angle <= pi: never cut
     const unsigned char *my_rec = stage + lane_id * CO_REC_STRIDE;        // this lane's staged cell record
     const unsigned long long l2pol = l2_policy_evict_last();
-    unsigned long long *fetch_list = reinterpret_cast<unsigned long long *>(stage + 32 * CO_REC_STRIDE);  // [32] per warp
+    unsigned char *fetch_list = stage + CO_LIST_OFS;                       // entry j at fetch_list + j * CO_LIST_STRIDE
+#if RWRT_POINT_FETCH
+    // quarter-warp lane q8 copies 16-byte half (q8 & 1) of sector i = 0..2 of corner point q8 >> 1
+    // (0: (x0,y0)  1: (x0,y1)  2: (x1,y0)  3: (x1,y1)); 3 sectors x 32 B = one 96-byte point
+    const unsigned pf_dst = (unsigned)((q8 >> 1) * 96 + (q8 & 1) * 16);
+    const long long pf_row_bytes = (long long)p.g.nlat * NPK * 8;         // from (x0, .) to (x1, .)
+#endif
 
     for (;;) {
         __syncwarp();
@@ -598,7 +629,9 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                         L.rejected = false;
                         L.fresh = true;
                         fb = member_base(p, L.slot);
+#if !RWRT_POINT_FETCH
                         fcb = p.g.fcell + (fb - p.g.fpk) / p.g.member_stride * p.g.cell_member_stride;
+#endif
                     }
                 }
             }
@@ -624,6 +657,48 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
         int x0, y0, x1, y1;
         double sx, sy;
         bool inr;
+#ifdef RWRT_DBG_SYNC
+#define RWRT_DBG_SYNC_STMT __syncwarp();
+#else
+#define RWRT_DBG_SYNC_STMT
+#endif
+#if RWRT_POINT_FETCH
+#define RWRT_FETCH(LON, LAT)                                                                                         \
+    {                                                                                                                \
+        inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
+        locate<RWRT_FAST>(p.g, LON, inr ? (LAT) : 0.0, x0, y0, x1, y1, sx, sy);                                      \
+        /* what is staged = point (x0, y0) AND the clamp pattern (interpolation.py:116-119: x1, y1 come from the     \
+           UNCLAMPED index, so a NaN / out-of-range position can pair (x0, y0) with x1 == x0); both go into the key */ \
+        const double *rec = reinterpret_cast<const double *>(                                                        \
+            reinterpret_cast<unsigned long long>(fb + ((size_t)x0 * p.g.nlat + y0) * NPK) | (x1 == x0 ? 2u : 0u) | (y1 == y0 ? 1u : 0u)); \
+        /* a ray often stays in its cell from one stage to the next: its corners are still staged, no new copy */   \
+        const bool need = (rec != prev_rec);                                                                         \
+        const unsigned need_mask = __ballot_sync(FULL, need);                                                        \
+        prev_rec = rec;                                                                                              \
+        /* compact list of the cells to fetch: entry = address of (x0,y0) (32-B aligned) | x clamped | y clamped | lane */ \
+        if (need)                                                                                                    \
+            *reinterpret_cast<unsigned long long *>(fetch_list + __popc(need_mask & ((1u << lane_id) - 1u)) * CO_LIST_STRIDE) = \
+                (reinterpret_cast<unsigned long long>(rec) >> 5 << 7) | ((reinterpret_cast<unsigned long long>(rec) & 3u) << 5) | (unsigned)lane_id; \
+        __syncwarp();                                                                                                \
+        const int nfetch = __popc(need_mask);                                                                        \
+        /* quarter-warp `grp` copies list entries grp, grp+4, ...: 24 x 16 B per cell */                             \
+        for (int j0 = 0; j0 < nfetch; j0 += 4) {                                                                     \
+            const int j = j0 + grp;                                                                                  \
+            if (j < nfetch) {                                                                                        \
+                const unsigned long long e = *reinterpret_cast<const unsigned long long *>(fetch_list + j * CO_LIST_STRIDE); \
+                const char *sp = reinterpret_cast<const char *>(e >> 7 << 5) + (q8 & 1) * 16;                        \
+                if ((q8 & 4) && !(e & 64u)) sp += pf_row_bytes;             /* corners 2, 3: x1 */                    \
+                if ((q8 & 2) && !(e & 32u)) sp += NPK * 8;                  /* corners 1, 3: y1 */                    \
+                const unsigned dst = stage_u32 + ((unsigned)e & 31u) * CO_REC_STRIDE + pf_dst;                       \
+                cp_async16(dst, sp, l2pol);                                                                          \
+                cp_async16(dst + 32, sp + 32, l2pol);                                                                \
+                cp_async16(dst + 64, sp + 64, l2pol);                                                                \
+            }                                                                                                        \
+        }                                                                                                            \
+        RWRT_DBG_SYNC_STMT                                                                                           \
+        asm volatile("cp.async.commit_group;\n" ::);                                                                 \
+    }
+#else
 #define RWRT_FETCH(LON, LAT)                                                                                         \
     {                                                                                                                \
         inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
@@ -635,14 +710,15 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
         prev_rec = rec;                                                                                              \
         /* compact list of the records to fetch: entry = record address | destination lane (records are 128-B aligned) */ \
         if (need)                                                                                                    \
-            fetch_list[__popc(need_mask & ((1u << lane_id) - 1u))] = reinterpret_cast<unsigned long long>(rec) | (unsigned)lane_id; \
+            *reinterpret_cast<unsigned long long *>(fetch_list + __popc(need_mask & ((1u << lane_id) - 1u)) * CO_LIST_STRIDE) = \
+                reinterpret_cast<unsigned long long>(rec) | (unsigned)lane_id;                                      \
         __syncwarp();                                                                                                \
         const int nfetch = __popc(need_mask);                                                                        \
         /* quarter-warp `grp` copies list entries grp, grp+4, ...; lane q8 moves chunk q8 of each of the 3 lines */   \
         for (int j0 = 0; j0 < nfetch; j0 += 4) {                                                                     \
             const int j = j0 + grp;                                                                                  \
             if (j < nfetch) {                                                                                        \
-                const unsigned long long e = fetch_list[j];                                                          \
+                const unsigned long long e = *reinterpret_cast<const unsigned long long *>(fetch_list + j * CO_LIST_STRIDE); \
                 const char *sp = reinterpret_cast<const char *>(e & ~127ull) + (q8 << 4);                            \
                 const unsigned dst = stage_u32 + ((unsigned)e & 31u) * CO_REC_STRIDE + (q8 << 4);                    \
                 cp_async16(dst, sp, l2pol);                                                                          \
@@ -652,6 +728,7 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
         }                                                                                                            \
         asm volatile("cp.async.commit_group;\n" ::);                                                                 \
     }
+#endif
         // stage 1 input (rkf45.py:306-311): y + (K_1 a_21) h
 #pragma unroll
         for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * cC[1][0]) * h;
@@ -718,7 +795,18 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                 wr.rden = wrden;
             }
             // blend (interpolation.py:132-133): a*wa + b*wb + c*wc + d*wd, fields k = 0..10
-            double f[11];
+            double f[12];
+#if RWRT_POINT_FETCH
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {   // corners c = (x0,y0), a = (x0,y1), d = (x1,y0), b = (x1,y1); fields 2k, 2k+1
+                const double2 c2 = *reinterpret_cast<const double2 *>(my_rec + k * 16);
+                const double2 a2 = *reinterpret_cast<const double2 *>(my_rec + 96 + k * 16);
+                const double2 d2 = *reinterpret_cast<const double2 *>(my_rec + 192 + k * 16);
+                const double2 b2 = *reinterpret_cast<const double2 *>(my_rec + 288 + k * 16);
+                f[2 * k] = a2.x * wa_ + b2.x * wb + c2.x * wc + d2.x * wd_;
+                if (2 * k + 1 < 11) f[2 * k + 1] = a2.y * wa_ + b2.y * wb + c2.y * wc + d2.y * wd_;
+            }
+#else
 #pragma unroll
             for (int k = 0; k < 11; ++k) {
                 const int qa = 2 * k, qc = 2 * k + 1;
@@ -726,6 +814,7 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                 const double2 cd = *reinterpret_cast<const double2 *>(my_rec + qc * 16);
                 f[k] = ab.x * wa_ + ab.y * wb + cd.x * wc + cd.y * wd_;
             }
+#endif
             masked = err;
             Merc m = mercator_from_fields<RWRT_FAST>(f, tgp);
             rhs_position<RWRT_FAST>(m, yp, wr, kn, ug, vg);               // kn[0], kn[1], ug, vg
@@ -870,7 +959,7 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
             L.slot = -1;
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
-                L.y[c] = (c < 2) ? 0.0 : 1.0;
+                L.y[c] = (c < 2) ? RWRT_BENIGN_POS(c) : 1.0;
                 k1[c] = 0.0;
             }
             L.h_abs = 1.0;

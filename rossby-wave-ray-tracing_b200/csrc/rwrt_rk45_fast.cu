@@ -28,6 +28,8 @@ void launch_rk4_fast(const RunParams &p, cudaStream_t s)
     if (p.N > 0 && p.nt > 1) fast::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
 }
 
+bool coop_needs_cell_table_fast() { return !RWRT_POINT_FETCH; }
+
 int occupancy_rk45_fast(bool coop)
 {
     int nb = 0;

@@ -28,6 +28,8 @@ void launch_rk4_strict(const RunParams &p, cudaStream_t s)
     if (p.N > 0 && p.nt > 1) strict::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
 }
 
+bool coop_needs_cell_table_strict() { return !RWRT_POINT_FETCH; }
+
 int occupancy_rk45_strict(bool coop)
 {
     int nb = 0;
