@@ -47,7 +47,6 @@ typedef enum {
 /* flags for rwrt_ray_run_rk45 */
 #define RWRT_MODE_FAST 0u   /* FMA contraction allowed (default)                              */
 #define RWRT_MODE_STRICT 1u /* every operation a separate IEEE double op, reference order    */
-#define RWRT_RECORD_LAYOUT 2u /* internal: keep trajectories as per-ray records (no transpose) */
 
 /* per-slot status codes written by rwrt_ray_run_rk45 (new, additive: the reference only has NaN) */
 #define RWRT_RAY_NO_ROOT 0   /* NaN root at t = 0: never propagates   */

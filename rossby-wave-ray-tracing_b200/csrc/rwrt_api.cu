@@ -66,8 +66,7 @@ struct rwrt_ctx {
     int sm_count = 0;
     bool ready = false;
     double lon0 = 0, dlon = 0, lat0 = 0, dlat = 0;
-    DevBuf fpk, fcell, scratch, trig, live, state, counters, blockcnt;
-    bool have_cells = false;
+    DevBuf fpk, scratch, trig, live, state, counters, blockcnt;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t aux = nullptr;  // side stream for work that is independent of the integrator
     bool timed = false;
@@ -86,8 +85,6 @@ struct rwrt_ctx {
         g.dlat = dlat;
         g.rdlon = 1.0 / dlon;
         g.rdlat = 1.0 / dlat;
-        g.fcell = have_cells ? (const double *)(fcell.p ? fcell.p : fpk.p) : nullptr;   // non-null selects the cooperative kernel
-        g.cell_member_stride = (size_t)nlon_f * nlat * NCELL;
         return g;
     }
 };
@@ -273,7 +270,6 @@ int rwrt_destroy(rwrt_handle h)
     if (!h) return RWRT_OK;
     cudaSetDevice(h->device);
     h->fpk.release();
-    h->fcell.release();
     h->scratch.release();
     h->trig.release();
     h->live.release();
@@ -300,30 +296,6 @@ static int set_coords(rwrt_handle h, const double *lon, const double *lat, cudaS
     h->dlon = c[1] - c[0];
     h->lat0 = c[2];
     h->dlat = c[3] - c[2];
-    return RWRT_OK;
-}
-
-// Cell-major copy of the packed fields for the cooperative-gather integrator: used when it stays
-// L2-resident (<= RWRT_CELL_LIMIT_MB, default 100 MB); larger grids keep the point-major kernel.
-static int build_cell_table(rwrt_handle h, cudaStream_t s)
-{
-    h->have_cells = false;
-    size_t bytes = (size_t)h->nmember * h->nlon_f * h->nlat * NCELL * sizeof(double);
-    size_t limit_mb = 100;
-    if (const char *e = getenv("RWRT_CELL_LIMIT_MB")) limit_mb = (size_t)atol(e);
-    if (!coop_needs_cell_table_fast() && !coop_needs_cell_table_strict()) {
-        // default build: the cooperative kernel gathers from the packed point table itself, no copy is needed;
-        // RWRT_CELL_LIMIT_MB=0 still selects the per-lane kernel (cross-check of the two gather implementations)
-        h->fcell.release();
-        h->have_cells = (limit_mb != 0);
-        return RWRT_OK;
-    }
-    if (bytes > limit_mb * 1024 * 1024) return RWRT_OK;
-    if (h->fcell.reserve(bytes)) return RWRT_OK;  // not fatal: fall back to the point-major kernel
-    Grid g = h->grid();
-    launch_build_cells(g, h->nmember, (double *)h->fcell.p, s);
-    CU(cudaGetLastError());
-    h->have_cells = true;
     return RWRT_OK;
 }
 
@@ -362,7 +334,7 @@ int rwrt_bs_ready(rwrt_handle h, const float *u, const float *v, const double *l
     launch_bs_ready(a, s);
     CU(cudaGetLastError());
     h->ready = true;
-    return build_cell_table(h, s);
+    return RWRT_OK;
 }
 
 int rwrt_bs_set_fields(rwrt_handle h, const double *fields18, const double *lon, const double *lat, void *stream)
@@ -375,7 +347,7 @@ int rwrt_bs_set_fields(rwrt_handle h, const double *fields18, const double *lon,
     launch_pack_from_fields18(h->nmember, h->nlon_f, h->nlat, fields18, (double *)h->fpk.p, s);
     CU(cudaGetLastError());
     h->ready = true;
-    return build_cell_table(h, s);
+    return RWRT_OK;
 }
 
 int rwrt_sample_mercator(rwrt_handle h, int64_t n, const double *lon, const double *lat, const int32_t *member,
@@ -496,7 +468,11 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
 
     // 3. launch: static slots, prepare, persistent integrator (one wave of resident blocks)
     bool strict = (flags & RWRT_MODE_STRICT) != 0;
-    const bool coop = p.g.fcell != nullptr;
+    // The cooperative-gather kernel is the product path for every grid; RWRT_PER_LANE_GATHER=1 selects the per-lane
+    // kernel instead (tests: two independent gather implementations must agree bit for bit).
+    bool coop = true;
+    if (const char *e = getenv("RWRT_PER_LANE_GATHER")) coop = (atoi(e) == 0);
+    p.coop = coop ? 1 : 0;
     int per_sm = strict ? occupancy_rk45_strict(coop) : occupancy_rk45_fast(coop);
     if (per_sm < 1) per_sm = 1;
     if (const char *e = getenv("RWRT_BLOCKS_PER_SM")) {  // tuning knob (profiles/): cap resident blocks per SM

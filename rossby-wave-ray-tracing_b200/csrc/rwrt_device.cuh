@@ -22,7 +22,6 @@ constexpr double REARTH = 6.3712e6;                                           //
 constexpr double OMEGA = 7.2921e-5;                                           // constants.py:17
 constexpr double DELT = 1.0e-8;                                               // constants.py:28
 constexpr int NPK = 12;  // doubles per packed grid point
-constexpr int NCELL = 48;  // doubles per cell record: 11 fields x 4 corners (a,b,c,d) + 4 pad = 384 B = 3 lines
 
 struct Grid {
     const double *fpk;     // (nmember, nlon_f, nlat, NPK)
@@ -30,8 +29,6 @@ struct Grid {
     int nlon_f, nlat;      // nlon_f = nlon + 1 when xcyclic (wrap column, bs.py:370-372)
     double lon0, dlon, lat0, dlat;  // lon[0], lon[1]-lon[0], lat[0], lat[1]-lat[0] (interpolation.py:78-79)
     double rdlon, rdlat;            // 1/dlon, 1/dlat (fast build only)
-    const double *fcell;            // optional cell-major table (nmember, nlon_f, nlat, NCELL) or nullptr
-    size_t cell_member_stride;      // doubles between members in fcell
 };
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }

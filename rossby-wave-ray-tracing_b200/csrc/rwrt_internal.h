@@ -17,10 +17,7 @@ void launch_rk45_window_strict(const RunParams &p, int integrate_blocks, cudaStr
 void launch_rk4_fast(const RunParams &p, cudaStream_t s);
 void launch_rk4_strict(const RunParams &p, cudaStream_t s);
 int occupancy_rk45_fast(bool coop);
-bool coop_needs_cell_table_fast();
-bool coop_needs_cell_table_strict();
 int occupancy_rk45_strict(bool coop);
-void launch_build_cells(const Grid &g, int nmember, double *fcell, cudaStream_t s);
 void launch_rhs_fast(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s);
 void launch_rhs_strict(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s);
 

@@ -399,44 +399,28 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
 
 
 // ---------------------------------------------------------------------------------------------
-// Cooperative-gather integrator (the default when the handle holds a cell-major field table).
+// Cooperative-gather integrator (the product path for every grid and ensemble size).
 //
 // v3 above is bound by the L1TEX wavefront pipe (profiles/r1_v3_*: 92 % of peak): every lane fetches
 // its own 4 corners x 96 B with 24 fully divergent LDG.128 per right-hand side.  Here the warp
-// fetches together: each ray's bilinear cell is ONE 384-byte record (11 fields x 4 corners, 3 cache
-// lines, line aligned), a quarter-warp copies one line of one ray with 8 contiguous 16-byte
-// cp.async (LDGSTS) -- 4 wavefronts per instruction instead of ~32 -- straight into a padded
-// shared-memory stage (no landing registers, all 24 copies of a stage in flight at once), and while
-// they fly the lanes evaluate sincos / the wavenumber reciprocals.  Each lane then reads its own
-// record back with conflict-free LDS.128.  Arithmetic and operation order are unchanged.
-// Shared memory per warp: 11.75 KB stage + 6.25 KB for K2..K6 -> 3 blocks of 128 threads per SM.
+// fetches together: a quarter-warp copies the four corner points of ONE ray's cell (4 x 96 B) with
+// 16-byte cp.async (LDGSTS) -- a handful of wavefronts per instruction instead of ~32 -- straight into a
+// padded shared-memory stage (no landing registers, all copies of a stage in flight at once), only for
+// the rays that changed cell since their last stage, and one stage AHEAD of use.  Each lane then reads its
+// own four points back with conflict-free LDS.128.  Arithmetic and operation order are unchanged.
+// Shared memory per warp: 12.5 KB stage + 6.25 KB for K2..K6 -> 76 800 B per block, 3 blocks per SM exactly.
 // ---------------------------------------------------------------------------------------------
-// RWRT_POINT_FETCH=1: the warp gathers the four corner points of a ray's cell straight from the packed POINT table
-// (4 x 96 B; the two latitude neighbours are contiguous) instead of one 384-byte record of a cell-major copy.
-// Same number of 16-byte copies per ray, but the table is 4x smaller (6.3 MB at 1 deg, 100 MB at 0.25 deg, 6.3 GB
-// for a 1000-member ensemble) -- so every configuration runs on this kernel and no cell table is built.
-#ifndef RWRT_POINT_FETCH
-#define RWRT_POINT_FETCH 1
-#endif
+// The warp gathers the four corner points of a ray's cell straight from the packed POINT table (4 x 96 B; the two
+// latitude neighbours are contiguous).  v4-v11 read one 384-byte record of a cell-major COPY of the table instead:
+// same number of 16-byte copies per ray and the same speed at 1 degree, but the copy was 4x the size (399 MB at
+// 0.25 degree, 25 GB for a 1000-member ensemble) and those configurations fell back to the per-lane kernel.
 #ifndef RWRT_BENIGN_POS
 #define RWRT_BENIGN_POS(c) 0.0   /* (lon, lat) of the state idle lanes run along on */
 #endif
-#if RWRT_POINT_FETCH
 constexpr int CO_REC_STRIDE = 400;   // 25 x 16 B per staged ray (4 points x 96 B + 16 B holding the fetch-list entry):
                                      // an odd number of 16-byte chunks, so a quarter-warp's LDS.128 / LDGSTS never conflict
-#ifdef RWRT_DBG_LIST
-constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE + 256;
-constexpr int CO_LIST_OFS = 32 * CO_REC_STRIDE, CO_LIST_STRIDE = 8;
-#else
 constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE;                         // per warp; 4 warps + K2..K6 = 76 800 B = 3 blocks / SM exactly
 constexpr int CO_LIST_OFS = 384, CO_LIST_STRIDE = CO_REC_STRIDE;           // fetch-list entry j sits in the pad of row j
-#endif
-#else
-constexpr int CO_REC_STRIDE = 368;   // 23 x 16 B per staged ray: chunk q of ray r sits in bank group (q - r) mod 8,
-                                     // so a quarter-warp's LDS.128 / LDGSTS never conflict -- no swizzle arithmetic
-constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE + 256;                   // per warp: records + fetch list
-constexpr int CO_LIST_OFS = 32 * CO_REC_STRIDE, CO_LIST_STRIDE = 8;
-#endif
 
 // Stage vectors K2..K6 (25 doubles per ray) live in TENSOR MEMORY: lane = thread, 10 x 32-bit columns per
 // stage vector, 64 columns per block.  That takes 6.25 KB per warp out of shared memory, which was what
@@ -511,9 +495,9 @@ __device__ __forceinline__ void tm_combo(unsigned tk, const double *k1, const do
     }
 }
 
-// The cell table (25 MB at 1 degree) must stay in L2 while 23 GB of trajectories stream through it: 13 % of the
-// record sectors missed L2 under the default policy, and since a warp waits for ~120 sectors per stage nearly every
-// wait paid a DRAM round trip.  Records are therefore fetched with an evict_last policy; the trajectory rows are
+// The field table must stay in L2 while 23 GB of trajectories stream through it: with the default policy 13 % of
+// the gathered sectors missed L2 (v11, cell-major table), and since a warp waits for ~50-120 sectors per stage nearly
+// every wait paid a DRAM round trip.  The gathers therefore carry an evict_last policy; the trajectory rows are
 // written once and never read back.
 #ifndef RWRT_L2_HINT
 #define RWRT_L2_HINT 1
@@ -570,9 +554,6 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     for (int c = 0; c < 5; ++c) L.y[c] = (c < 2) ? RWRT_BENIGN_POS(c) : 1.0;              // benign state for idle lanes
     L.h_abs = 1.0;
     L.t = 0.0;
-#if !RWRT_POINT_FETCH
-    const double *fcb = p.g.fcell;
-#endif
     const double *fb = p.g.fpk;
     bool queue_empty = false;
     long long my_total = 0;
@@ -585,12 +566,10 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     const unsigned char *my_rec = stage + lane_id * CO_REC_STRIDE;        // this lane's staged cell record
     const unsigned long long l2pol = l2_policy_evict_last();
     unsigned char *fetch_list = stage + CO_LIST_OFS;                       // entry j at fetch_list + j * CO_LIST_STRIDE
-#if RWRT_POINT_FETCH
     // quarter-warp lane q8 copies 16-byte half (q8 & 1) of sector i = 0..2 of corner point q8 >> 1
     // (0: (x0,y0)  1: (x0,y1)  2: (x1,y0)  3: (x1,y1)); 3 sectors x 32 B = one 96-byte point
     const unsigned pf_dst = (unsigned)((q8 >> 1) * 96 + (q8 & 1) * 16);
     const long long pf_row_bytes = (long long)p.g.nlat * NPK * 8;         // from (x0, .) to (x1, .)
-#endif
 
     for (;;) {
         __syncwarp();
@@ -629,9 +608,6 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                         L.rejected = false;
                         L.fresh = true;
                         fb = member_base(p, L.slot);
-#if !RWRT_POINT_FETCH
-                        fcb = p.g.fcell + (fb - p.g.fpk) / p.g.member_stride * p.g.cell_member_stride;
-#endif
                     }
                 }
             }
@@ -657,12 +633,6 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
         int x0, y0, x1, y1;
         double sx, sy;
         bool inr;
-#ifdef RWRT_DBG_SYNC
-#define RWRT_DBG_SYNC_STMT __syncwarp();
-#else
-#define RWRT_DBG_SYNC_STMT
-#endif
-#if RWRT_POINT_FETCH
 #define RWRT_FETCH(LON, LAT)                                                                                         \
     {                                                                                                                \
         inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
@@ -695,40 +665,8 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                 cp_async16(dst + 64, sp + 64, l2pol);                                                                \
             }                                                                                                        \
         }                                                                                                            \
-        RWRT_DBG_SYNC_STMT                                                                                           \
         asm volatile("cp.async.commit_group;\n" ::);                                                                 \
     }
-#else
-#define RWRT_FETCH(LON, LAT)                                                                                         \
-    {                                                                                                                \
-        inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
-        locate<RWRT_FAST>(p.g, LON, inr ? (LAT) : 0.0, x0, y0, x1, y1, sx, sy);                                      \
-        const double *rec = fcb + ((size_t)x0 * p.g.nlat + y0) * NCELL;                                              \
-        /* a ray often stays in its cell from one stage to the next: its record is still staged, no new copy */     \
-        const bool need = (rec != prev_rec);                                                                         \
-        const unsigned need_mask = __ballot_sync(FULL, need);                                                        \
-        prev_rec = rec;                                                                                              \
-        /* compact list of the records to fetch: entry = record address | destination lane (records are 128-B aligned) */ \
-        if (need)                                                                                                    \
-            *reinterpret_cast<unsigned long long *>(fetch_list + __popc(need_mask & ((1u << lane_id) - 1u)) * CO_LIST_STRIDE) = \
-                reinterpret_cast<unsigned long long>(rec) | (unsigned)lane_id;                                      \
-        __syncwarp();                                                                                                \
-        const int nfetch = __popc(need_mask);                                                                        \
-        /* quarter-warp `grp` copies list entries grp, grp+4, ...; lane q8 moves chunk q8 of each of the 3 lines */   \
-        for (int j0 = 0; j0 < nfetch; j0 += 4) {                                                                     \
-            const int j = j0 + grp;                                                                                  \
-            if (j < nfetch) {                                                                                        \
-                const unsigned long long e = *reinterpret_cast<const unsigned long long *>(fetch_list + j * CO_LIST_STRIDE); \
-                const char *sp = reinterpret_cast<const char *>(e & ~127ull) + (q8 << 4);                            \
-                const unsigned dst = stage_u32 + ((unsigned)e & 31u) * CO_REC_STRIDE + (q8 << 4);                    \
-                cp_async16(dst, sp, l2pol);                                                                          \
-                cp_async16(dst + 128, sp + 128, l2pol);                                                              \
-                if (q8 < 6) cp_async16(dst + 256, sp + 256, l2pol);        /* chunks 22, 23 of a record are padding */ \
-            }                                                                                                        \
-        }                                                                                                            \
-        asm volatile("cp.async.commit_group;\n" ::);                                                                 \
-    }
-#endif
         // stage 1 input (rkf45.py:306-311): y + (K_1 a_21) h
 #pragma unroll
         for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * cC[1][0]) * h;
@@ -796,7 +734,6 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
             }
             // blend (interpolation.py:132-133): a*wa + b*wb + c*wc + d*wd, fields k = 0..10
             double f[12];
-#if RWRT_POINT_FETCH
 #pragma unroll
             for (int k = 0; k < 6; ++k) {   // corners c = (x0,y0), a = (x0,y1), d = (x1,y0), b = (x1,y1); fields 2k, 2k+1
                 const double2 c2 = *reinterpret_cast<const double2 *>(my_rec + k * 16);
@@ -806,15 +743,6 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                 f[2 * k] = a2.x * wa_ + b2.x * wb + c2.x * wc + d2.x * wd_;
                 if (2 * k + 1 < 11) f[2 * k + 1] = a2.y * wa_ + b2.y * wb + c2.y * wc + d2.y * wd_;
             }
-#else
-#pragma unroll
-            for (int k = 0; k < 11; ++k) {
-                const int qa = 2 * k, qc = 2 * k + 1;
-                const double2 ab = *reinterpret_cast<const double2 *>(my_rec + qa * 16);
-                const double2 cd = *reinterpret_cast<const double2 *>(my_rec + qc * 16);
-                f[k] = ab.x * wa_ + ab.y * wb + cd.x * wc + cd.y * wd_;
-            }
-#endif
             masked = err;
             Merc m = mercator_from_fields<RWRT_FAST>(f, tgp);
             rhs_position<RWRT_FAST>(m, yp, wr, kn, ug, vg);               // kn[0], kn[1], ug, vg
@@ -979,32 +907,6 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     for (int o = 16; o > 0; o >>= 1) my_total += __shfl_down_sync(FULL, my_total, o);
     if (lane_id == 0 && my_total) atomicAdd(p.total_accepted, (unsigned long long)my_total);
 }
-
-// Cell-major table: record (x0, y0) = for k in 0..10: a = F[x0][y1], b = F[x1][y1], c = F[x0][y0], d = F[x1][y0]
-// with x1 = min(x0+1, W-1), y1 = min(y0+1, H-1) (the clamps of interpolation.py:116-119 baked in).
-__global__ void __launch_bounds__(256) build_cells_kernel(Grid g, int nmember, double *fcell)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int W = g.nlon_f, H = g.nlat;
-    size_t ncell = (size_t)nmember * W * H;
-    if (i >= ncell) return;
-    int y0 = (int)(i % H);
-    size_t t = i / H;
-    int x0 = (int)(t % W), m = (int)(t / W);
-    int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-    const double *fb = g.fpk + (size_t)m * g.member_stride;
-    const double *pa = fb + ((size_t)x0 * H + y1) * NPK, *pb = fb + ((size_t)x1 * H + y1) * NPK;
-    const double *pc = fb + ((size_t)x0 * H + y0) * NPK, *pd = fb + ((size_t)x1 * H + y0) * NPK;
-    double *o = fcell + i * NCELL;
-    for (int k = 0; k < 11; ++k) {
-        o[4 * k + 0] = pa[k];
-        o[4 * k + 1] = pb[k];
-        o[4 * k + 2] = pc[k];
-        o[4 * k + 3] = pd[k];
-    }
-    for (int k = 44; k < NCELL; ++k) o[k] = 0.0;
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // Fixed-step RK4 path: WR.core_ray_run_numpy (wr.py:702-765) with rk4_step_numpy (wr.py:583-622) and

@@ -13,12 +13,12 @@ void launch_rk45_setup_fast(const RunParams &p, int prepare_blocks, int fill_blo
         fast::fill_static_slots<<<dim3(fill_blocks, p.nt - 1 < 24 ? p.nt - 1 : 24), 256, 0, aux>>>(p);
 }
 
-// One time window [p.it_begin, p.it_end) of output rows for every live ray (the point-major kernel has no
+// One time window [p.it_begin, p.it_end) of output rows for every live ray (the per-lane kernel has no
 // windows: it is launched once with the whole range).
 void launch_rk45_window_fast(const RunParams &p, int integrate_blocks, cudaStream_t s)
 {
     if (p.nlive <= 0) return;
-    if (p.g.fcell)
+    if (p.coop)
         fast::rk45_integrate_coop<<<integrate_blocks, fast::RK_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
     else
         fast::rk45_integrate<<<integrate_blocks, fast::RK_THREADS, fast::RK_SMEM_BYTES, s>>>(p);
@@ -27,8 +27,6 @@ void launch_rk4_fast(const RunParams &p, cudaStream_t s)
 {
     if (p.N > 0 && p.nt > 1) fast::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
 }
-
-bool coop_needs_cell_table_fast() { return !RWRT_POINT_FETCH; }
 
 int occupancy_rk45_fast(bool coop)
 {
@@ -60,10 +58,5 @@ __global__ void rhs_kernel_fast(Grid g, long long n, const double *y, const int3
 void launch_rhs_fast(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s)
 {
     if (n > 0) rhs_kernel_fast<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, n, y, member, dy);
-}
-void launch_build_cells(const Grid &g, int nmember, double *fcell, cudaStream_t s)
-{
-    size_t ncell = (size_t)nmember * g.nlon_f * g.nlat;
-    fast::build_cells_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(g, nmember, fcell);
 }
 }  // namespace rwrt

@@ -16,6 +16,7 @@ struct RunParams {
     const int32_t *live;        // compacted list of live slots
     long long nlive;
     double *state;              // (nlive, RWRT_STATE): y[5], f[5], h_abs, cos(prev lat), t, prev lon, prev lat, counters
+    int coop;                   // 1: cooperative-gather integrator (default); 0: per-lane gather (cross-check)
     int it_begin, it_end;       // this launch produces output rows [it_begin, it_end) (time window)
     long long *accepted;        // (N) or nullptr
     long long *attempts;        // (N) or nullptr

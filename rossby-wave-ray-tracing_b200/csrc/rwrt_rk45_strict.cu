@@ -13,12 +13,12 @@ void launch_rk45_setup_strict(const RunParams &p, int prepare_blocks, int fill_b
         strict::fill_static_slots<<<dim3(fill_blocks, p.nt - 1 < 24 ? p.nt - 1 : 24), 256, 0, aux>>>(p);
 }
 
-// One time window [p.it_begin, p.it_end) of output rows for every live ray (the point-major kernel has no
+// One time window [p.it_begin, p.it_end) of output rows for every live ray (the per-lane kernel has no
 // windows: it is launched once with the whole range).
 void launch_rk45_window_strict(const RunParams &p, int integrate_blocks, cudaStream_t s)
 {
     if (p.nlive <= 0) return;
-    if (p.g.fcell)
+    if (p.coop)
         strict::rk45_integrate_coop<<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
     else
         strict::rk45_integrate<<<integrate_blocks, strict::RK_THREADS, strict::RK_SMEM_BYTES, s>>>(p);
@@ -27,8 +27,6 @@ void launch_rk4_strict(const RunParams &p, cudaStream_t s)
 {
     if (p.N > 0 && p.nt > 1) strict::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
 }
-
-bool coop_needs_cell_table_strict() { return !RWRT_POINT_FETCH; }
 
 int occupancy_rk45_strict(bool coop)
 {

@@ -321,10 +321,10 @@ def test_ensemble_members_match_single_runs():
         assert np.array_equal(got_acc[:, idx, :], w.accepted)
 
 
-def test_quarter_degree_grid_point_major_kernel():
-    """BASELINE configs[4] in miniature: 0.25-degree grid (cell table would be 399 MB -> the point-major
-    kernel is used), a few hundred sources, against the oracle on its non-grazing set; also checks that
-    the two integrators (cooperative cell gather / per-lane point gather) agree bit for bit on a 1-degree case."""
+def test_quarter_degree_grid_and_gather_cross_check():
+    """BASELINE configs[4] in miniature: 0.25-degree grid (100 MB point table), a few hundred sources, against
+    the oracle on its non-grazing set; also checks that the two integrators (warp-cooperative gather / per-lane
+    gather: independent implementations of the sampler) agree bit for bit on a 1-degree and on the 0.25-degree case."""
     import os
     u, v = synthetic.clim(1440, 721)
     sl, sa = synthetic.random_sources(120, 123)
@@ -340,15 +340,23 @@ def test_quarter_degree_grid_point_major_kernel():
     u2, v2 = synthetic.clim(360, 181)
     w1 = make_wr(u2, v2, zwn, slon, slat, 6.0)
     w1.ray_run(mode="numpy", inte_method="rk45", strict=True)
-    os.environ["RWRT_CELL_LIMIT_MB"] = "0"
+    os.environ["RWRT_PER_LANE_GATHER"] = "1"
     try:
         w2 = make_wr(u2, v2, zwn, slon, slat, 6.0)
         w2.ray_run(mode="numpy", inte_method="rk45", strict=True)
     finally:
-        del os.environ["RWRT_CELL_LIMIT_MB"]
+        del os.environ["RWRT_PER_LANE_GATHER"]
     for n in parity.NAMES:
         assert np.array_equal(getattr(w1, n), getattr(w2, n), equal_nan=True), n
     assert np.array_equal(w1.accepted, w2.accepted)
+    os.environ["RWRT_PER_LANE_GATHER"] = "1"
+    try:
+        w3 = make_wr(u, v, zwn, slon, slat, 6.0)
+        w3.ray_run(mode="numpy", inte_method="rk45", strict=True)
+    finally:
+        del os.environ["RWRT_PER_LANE_GATHER"]
+    for n in parity.NAMES:
+        assert np.array_equal(getattr(w, n), getattr(w3, n), equal_nan=True), ("quarter-degree", n)
 
 
 def test_frequency_sweep_with_gridding():
