@@ -93,7 +93,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
+
+    def mark(self):
+        """Start of the timed region: only samples that arrive after this count (nvidia-smi needs ~1 s to start,
+        so the sampler itself is started before the warm-up)."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -104,7 +109,12 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        rows = [r[1:] for r in self.rows if r[0] >= t_mark]
+        window = "timed region"
+        if not rows:   # timed region shorter than one sampling period: the last samples of the (identical) warm-up load
+            rows, window = [r[1:] for r in self.rows[-5:]], "warm-up (timed region shorter than the sampling period)"
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -113,7 +123,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -234,15 +244,16 @@ def run_ours(a):
                                       lib.ptr(out), lib.ptr(acc), None, None, lib.ptr(total), sp), "rwrt_ray_run_rk45")
 
     stats = (C.c_double * 3)()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(a.warmup):
         one_step()
         flush.zero_()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     kern_ms, steps_done, launches = [], 0, 0
     torch.cuda.synchronize()
