@@ -174,6 +174,21 @@ int rwrt_last_run_stats(rwrt_handle h, double *stats3);
  * chains).  Diagnostic only; used by bench.py next to MEASURED_PEAKS.json, which has no FP64 figure. */
 int rwrt_measure_fp64_peak(rwrt_handle h, double *tflops);
 
+/*
+ * SHSF.SHSF(data, truncation_level, sampling) (SHSF.py:10-33): the reference's optional pre-filter of the background
+ * winds -- spherical-harmonic analysis of a Driscoll-Healy grid (pyshtools SHExpandDH), triangular truncation
+ * (SHCoeffs.pad) and synthesis (MakeGridDH, whose default sampling = 1 makes the OUTPUT an n x n grid with
+ * n = 2 * truncation + 2, whatever the input was).  pyshtools is an un-vendored dependency: parity unpinned, the
+ * published algorithm is restated.  A plan holds the transform tables for one (nlat, truncation).
+ *   grid: (nmember, nlat, in_sampling * nlat) float64 device, row 0 = north pole, longitude 0 first;
+ *   out : (nmember, nlat_out, nlon_out) float64 device, nlat_out = 2 * truncation + 2, nlon_out = out_sampling * nlat_out.
+ */
+typedef struct rwrt_shsf_plan_s *rwrt_shsf_plan;
+int rwrt_shsf_plan_create(int device, int nlat, int in_sampling, int truncation, int out_sampling, rwrt_shsf_plan *out);
+int rwrt_shsf_out_shape(rwrt_shsf_plan p, int *nlat_out, int *nlon_out);
+int rwrt_shsf_apply(rwrt_shsf_plan p, const double *grid, int nmember, double *out, void *stream);
+int rwrt_shsf_plan_destroy(rwrt_shsf_plan p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ UNITS = {
     "rwrt_grid.cu": ["-fmad=false"],
     "rwrt_rk45_fast.cu": [],
     "rwrt_rk45_strict.cu": ["-fmad=false"],
+    "rwrt_shsf.cu": [],
 }
 
 
@@ -52,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in _deps()):
         return LIB
     log = []
-    with ThreadPoolExecutor(max_workers=6) as ex:
+    with ThreadPoolExecutor(max_workers=7) as ex:
         objs = list(ex.map(lambda kv: _compile(kv[0], kv[1], log), UNITS.items()))
     cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -71,7 +72,7 @@ def build_variant(out: str, extra: list) -> str:
     objdir = out + ".obj"
     os.makedirs(objdir, exist_ok=True)
     log = []
-    with ThreadPoolExecutor(max_workers=6) as ex:
+    with ThreadPoolExecutor(max_workers=7) as ex:
         objs = list(ex.map(lambda kv: _compile(kv[0], kv[1] + extra, log, objdir), UNITS.items()))
     r = subprocess.run([NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:

@@ -61,6 +61,10 @@ struct DevBuf {
 
 }  // namespace
 
+namespace rwrt {
+void set_error_string(const std::string &s) { g_err = s; }   // for the other translation units (rwrt_shsf.cu)
+}  // namespace rwrt
+
 struct rwrt_ctx {
     int device = 0, nlon = 0, nlat = 0, xcyclic = 1, nmember = 1, nlon_f = 0;
     int sm_count = 0;
