@@ -476,6 +476,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     // kernel instead (tests: two independent gather implementations must agree bit for bit).
     bool coop = true;
     if (const char *e = getenv("RWRT_PER_LANE_GATHER")) coop = (atoi(e) == 0);
+    if ((long long)h->nmember * h->nlon_f * h->nlat >= (1LL << 30) - 1) coop = false;  // its fetch keys hold 30-bit point indices (103 GB of fields)
     p.coop = coop ? 1 : 0;
     int per_sm = strict ? occupancy_rk45_strict(coop) : occupancy_rk45_fast(coop);
     if (per_sm < 1) per_sm = 1;

@@ -559,7 +559,8 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     long long my_total = 0;
     const int q8 = lane_id & 7, grp = lane_id >> 3;
     double pcos = 1.0;                                                     // cos(latitude of the previous output)
-    const double *prev_rec = nullptr;                                      // cell record currently staged for this lane
+    unsigned prev_key = 0xffffffffu;                                       // what is staged for this lane: point index | clamp pattern
+    unsigned member_pt = 0;                                                // first point of this lane's ensemble member
     long long my_ray = -1;                                                 // index of this lane's ray in the state array
     int acc0 = 0;                                                          // accepted steps when this launch picked the ray up
     const double shc = sin(0.5 * p.cut), sin2_half_cut = (p.cut >= PI) ? 2.0 : shc * shc;  // angle <= pi: never cut
@@ -568,8 +569,10 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     unsigned char *fetch_list = stage + CO_LIST_OFS;                       // entry j at fetch_list + j * CO_LIST_STRIDE
     // quarter-warp lane q8 copies 16-byte half (q8 & 1) of sector i = 0..2 of corner point q8 >> 1
     // (0: (x0,y0)  1: (x0,y1)  2: (x1,y0)  3: (x1,y1)); 3 sectors x 32 B = one 96-byte point
-    const unsigned pf_dst = (unsigned)((q8 >> 1) * 96 + (q8 & 1) * 16);
-    const long long pf_row_bytes = (long long)p.g.nlat * NPK * 8;         // from (x0, .) to (x1, .)
+    const unsigned pf_dst = stage_u32 + (unsigned)((q8 >> 1) * 96 + (q8 & 1) * 16);
+    const unsigned pf_dx = (q8 & 4) ? (unsigned)p.g.nlat * NPK * 8 : 0u;  // corners 2, 3 live one longitude row further
+    const unsigned pf_dy = (q8 & 2) ? NPK * 8u : 0u;                      // corners 1, 3 one point further
+    const char *pf_src = reinterpret_cast<const char *>(p.g.fpk) + (q8 & 1) * 16 + pf_dx + pf_dy;
 
     for (;;) {
         __syncwarp();
@@ -608,6 +611,7 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                         L.rejected = false;
                         L.fresh = true;
                         fb = member_base(p, L.slot);
+                        member_pt = (unsigned)((fb - p.g.fpk) / NPK);
                     }
                 }
             }
@@ -637,33 +641,34 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     {                                                                                                                \
         inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
         locate<RWRT_FAST>(p.g, LON, inr ? (LAT) : 0.0, x0, y0, x1, y1, sx, sy);                                      \
-        /* what is staged = point (x0, y0) AND the clamp pattern (interpolation.py:116-119: x1, y1 come from the     \
-           UNCLAMPED index, so a NaN / out-of-range position can pair (x0, y0) with x1 == x0); both go into the key */ \
-        const double *rec = reinterpret_cast<const double *>(                                                        \
-            reinterpret_cast<unsigned long long>(fb + ((size_t)x0 * p.g.nlat + y0) * NPK) | (x1 == x0 ? 2u : 0u) | (y1 == y0 ? 1u : 0u)); \
+        /* what gets staged = point (x0, y0) AND the clamp pattern (interpolation.py:116-119: x1, y1 come from the   \
+           UNCLAMPED index, so a NaN / out-of-range position can pair (x0, y0) with x1 == x0); both are in the key: \
+           bits 0..29 point index in the table (all members), bit 30 x clamped, bit 31 y clamped */                  \
+        const unsigned key = (member_pt + (unsigned)(x0 * p.g.nlat + y0)) | (x1 == x0 ? 0x40000000u : 0u) |          \
+                             (y1 == y0 ? 0x80000000u : 0u);                                                          \
         /* a ray often stays in its cell from one stage to the next: its corners are still staged, no new copy */   \
-        const bool need = (rec != prev_rec);                                                                         \
+        const bool need = (key != prev_key);                                                                         \
         const unsigned need_mask = __ballot_sync(FULL, need);                                                        \
-        prev_rec = rec;                                                                                              \
-        /* compact list of the cells to fetch: entry = address of (x0,y0) (32-B aligned) | x clamped | y clamped | lane */ \
+        prev_key = key;                                                                                              \
+        /* compact list of the cells to fetch: (key, destination lane) */                                            \
         if (need)                                                                                                    \
-            *reinterpret_cast<unsigned long long *>(fetch_list + __popc(need_mask & ((1u << lane_id) - 1u)) * CO_LIST_STRIDE) = \
-                (reinterpret_cast<unsigned long long>(rec) >> 5 << 7) | ((reinterpret_cast<unsigned long long>(rec) & 3u) << 5) | (unsigned)lane_id; \
+            *reinterpret_cast<uint2 *>(fetch_list + __popc(need_mask & ((1u << lane_id) - 1u)) * CO_LIST_STRIDE) =   \
+                make_uint2(key, (unsigned)lane_id * CO_REC_STRIDE);                                                  \
         __syncwarp();                                                                                                \
         const int nfetch = __popc(need_mask);                                                                        \
-        /* quarter-warp `grp` copies list entries grp, grp+4, ...: 24 x 16 B per cell */                             \
-        for (int j0 = 0; j0 < nfetch; j0 += 4) {                                                                     \
-            const int j = j0 + grp;                                                                                  \
-            if (j < nfetch) {                                                                                        \
-                const unsigned long long e = *reinterpret_cast<const unsigned long long *>(fetch_list + j * CO_LIST_STRIDE); \
-                const char *sp = reinterpret_cast<const char *>(e >> 7 << 5) + (q8 & 1) * 16;                        \
-                if ((q8 & 4) && !(e & 64u)) sp += pf_row_bytes;             /* corners 2, 3: x1 */                    \
-                if ((q8 & 2) && !(e & 32u)) sp += NPK * 8;                  /* corners 1, 3: y1 */                    \
-                const unsigned dst = stage_u32 + ((unsigned)e & 31u) * CO_REC_STRIDE + pf_dst;                       \
-                cp_async16(dst, sp, l2pol);                                                                          \
-                cp_async16(dst + 32, sp + 32, l2pol);                                                                \
-                cp_async16(dst + 64, sp + 64, l2pol);                                                                \
+        /* quarter-warp `grp` copies list entries grp, grp+4, ...: lane q8 moves 16-byte half (q8 & 1) of the three  \
+           sectors of corner q8 >> 1 -- 24 x 16 B per cell */                                                        \
+        for (int j = grp; j < nfetch; j += 4) {                                                                      \
+            const uint2 e = *reinterpret_cast<const uint2 *>(fetch_list + j * CO_LIST_STRIDE);                       \
+            const char *sp = pf_src + (size_t)(e.x & 0x3fffffffu) * (NPK * 8);                                       \
+            if (e.x >> 30) {                                                /* clamped: the far corner is the near one */ \
+                if (e.x & 0x40000000u) sp -= pf_dx;                                                                  \
+                if (e.x & 0x80000000u) sp -= pf_dy;                                                                  \
             }                                                                                                        \
+            const unsigned dst = pf_dst + e.y;                                                                       \
+            cp_async16(dst, sp, l2pol);                                                                              \
+            cp_async16(dst + 32, sp + 32, l2pol);                                                                    \
+            cp_async16(dst + 64, sp + 64, l2pol);                                                                    \
         }                                                                                                            \
         asm volatile("cp.async.commit_group;\n" ::);                                                                 \
     }
