@@ -63,6 +63,23 @@ def workload(name, rank=0):
         stride = 8 if name == "c5" else 128
         slon, slat = slon[rank % stride::stride], slat[rank % stride::stride]
         zwn, days = np.arange(1.0, 7.0), 60.0
+    elif name in ("c4", "c4-full"):
+        # BASELINE configs[3]: 1000-member ensemble of perturbed 1 deg backgrounds, 56 sources x k=1..6 x 3 roots
+        # (1008 ray slots) per member.  c4 = one GPU's share of the 8-GPU run (125 members, offset by rank);
+        # c4-full = all 1000 members on one GPU (6.3 GB of packed fields, 1.0 M slots).
+        nlon, nlat = 360, 181
+        nmem = 125 if name == "c4" else 1000
+        first = (rank % 8) * 125 if name == "c4" else 0
+        mem = [synthetic.ensemble_member(first + e, nlon, nlat) for e in range(nmem)]
+        u, v = np.stack([m[0] for m in mem]), np.stack([m[1] for m in mem])
+        rng = np.random.default_rng(4)
+        slon = np.tile(rng.uniform(0.0, 360.0, 56), nmem)
+        slat = np.tile(rng.uniform(-70.0, 70.0, 56), nmem)
+        member_of = np.repeat(np.arange(nmem, dtype=np.int32), 56)
+        zwn, days = np.arange(1.0, 7.0), 30.0
+        lon, lat = synthetic.grid_coords(nlon, nlat)
+        return dict(u=u, v=v, lon=lon, lat=lat, src_lon_deg=slon, src_lat_deg=slat, zwn=zwn, days=days,
+                    nlon=nlon, nlat=nlat, member_of=member_of, nmember=nmem)
     else:
         raise SystemExit(f"unknown workload {name}")
     lon, lat = synthetic.grid_coords(nlon, nlat)
@@ -224,12 +241,18 @@ def run_ours(a):
     flags = lib.MODE_STRICT if a.strict else lib.MODE_FAST
 
     h = lib.vp()
-    lib.check(L.rwrt_create(local, nlon, nlat, 1, 1, C.byref(h)), "rwrt_create")
+    nmember = int(wl.get("nmember", 1))
+    lib.check(L.rwrt_create(local, nlon, nlat, 1, nmember, C.byref(h)), "rwrt_create")
     stream = torch.cuda.current_stream()
     sp = lib.vp(stream.cuda_stream)
     d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
          dict(u=wl["u"], v=wl["v"], lon=wl["lon"], lat=wl["lat"], cl=np.cos(wl["lat"]), sl=np.sin(wl["lat"]),
               slon=slon, slat=slat, zwn=wl["zwn"]).items()}
+    mem_ptr = None
+    if "member_of" in wl:
+        d["mem"] = torch.from_numpy(np.ascontiguousarray(wl["member_of"])).to(dev)
+        mem_ptr = lib.ptr(d["mem"])
+        a.no_e2e = a.no_cpu = True                          # the host-pointer entry and the CPU sample are single-member
     lib.check(L.rwrt_bs_ready(h, lib.ptr(d["u"]), lib.ptr(d["v"]), lib.ptr(d["lon"]), lib.ptr(d["lat"]),
                               lib.ptr(d["cl"]), lib.ptr(d["sl"]), None, None, sp), "rwrt_bs_ready")
     out = torch.empty((7, nt, N), dtype=torch.float64, device=dev)
@@ -238,9 +261,9 @@ def run_ours(a):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def one_step():
-        lib.check(L.rwrt_ray_init(h, nsource, lib.ptr(d["slon"]), lib.ptr(d["slat"]), None, nzwn, lib.ptr(d["zwn"]),
+        lib.check(L.rwrt_ray_init(h, nsource, lib.ptr(d["slon"]), lib.ptr(d["slat"]), mem_ptr, nzwn, lib.ptr(d["zwn"]),
                                   0.0, nt, lib.ptr(out), sp), "rwrt_ray_init")
-        lib.check(L.rwrt_ray_run_rk45(h, nsource, None, nzwn, nt, tstep, ttotal, 1e-6, 1e-6, 1e-3, 0.1, flags,
+        lib.check(L.rwrt_ray_run_rk45(h, nsource, mem_ptr, nzwn, nt, tstep, ttotal, 1e-6, 1e-6, 1e-3, 0.1, flags,
                                       lib.ptr(out), lib.ptr(acc), None, None, lib.ptr(total), sp), "rwrt_ray_run_rk45")
 
     stats = (C.c_double * 3)()
@@ -329,9 +352,9 @@ def run_ours(a):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{a.workload}: Clim {360.0 / nlon:g}deg background, {nsource} sources x k=1..{nzwn} x 3 roots = {N} "
-                                   f"ray slots per GPU, {wl['days']:.0f} d, tstep 2 h, nt={nt}, rtol=atol=1e-6",
+                                   f"ray slots per GPU, {wl['days']:.0f} d, tstep 2 h, nt={nt}, rtol=atol=1e-6" + (f", {nmember} ensemble members" if nmember > 1 else ""),
                        "mode": "strict" if a.strict else "fast", "accepted_steps_per_step_per_gpu": steps_per_launch,
-                       "l2": "flushed between timed iterations (256 MB write); outputs (23 GB) exceed L2 anyway",
+                       "l2": f"flushed between timed iterations (256 MB write); outputs ({7 * nt * N * 8 / 1e9:.1f} GB) exceed L2 anyway",
                        "timed_region": "rwrt_ray_init + rwrt_ray_run_rk45 (fields resident in HBM)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -132,3 +132,37 @@ def test_c2_full_size_properties(monkeypatch):
         assert _checksum(out) == ck and total3 == total and torch.equal(acc, acc0)
     finally:
         L.rwrt_destroy(h)
+
+
+def test_schedule_and_gather_independence(monkeypatch):
+    """A quarter of C2 (287 k slots): the result may not depend on how rays are scheduled onto lanes (resident
+    blocks per SM, time windows) -- any stale or racing use of a warp's shared staging rows would show up here --
+    and, in the strict build, the warp-cooperative gather must agree bit for bit with the per-lane gather kernel
+    (two independent implementations of interpolation.py:103-135)."""
+    nlon, nlat = 360, 181
+    slon_deg, slat_deg = synthetic.all_gridpoint_sources(nlon, nlat, 88.0)
+    slon_deg, slat_deg = slon_deg[1::4], slat_deg[1::4]
+    zwn = np.arange(1.0, 7.0)
+    ns, nz = len(slon_deg), len(zwn)
+    L, h, d, dev = _setup(nlon, nlat, slon_deg, slat_deg, zwn)
+    try:
+        for flags in (lib.MODE_FAST, lib.MODE_STRICT):
+            out, acc, status, total, nt, N = _run(L, h, d, dev, ns, nz, flags)
+            ck, acc0 = _checksum(out), acc.clone()
+            del out
+            variants = [{"RWRT_BLOCKS_PER_SM": "1"}, {"RWRT_BLOCKS_PER_SM": "2"},
+                        {"RWRT_BLOCKS_PER_SM": "2", "RWRT_WINDOWS": "4"}, {"RWRT_WINDOWS": "9"}]
+            if flags == lib.MODE_STRICT:
+                variants.append({"RWRT_PER_LANE_GATHER": "1"})
+            for env in variants:
+                for k, v in env.items():
+                    monkeypatch.setenv(k, v)
+                try:
+                    out, acc, status, total2, _, _ = _run(L, h, d, dev, ns, nz, flags)
+                finally:
+                    for k in env:
+                        monkeypatch.delenv(k)
+                assert _checksum(out) == ck and total2 == total and bool((acc == acc0).all()), (flags, env)
+                del out
+    finally:
+        L.rwrt_destroy(h)
