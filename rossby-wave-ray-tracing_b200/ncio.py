@@ -97,7 +97,8 @@ def write_bsfile(path, lon, lat, fields):
         kw = dict(zlib=True, complevel=4) if kind == "nc4" else {}
         var = ds.createVariable(name, "f8", ("lon", "lat"), **kw)
         var[:, :] = np.asarray(data, dtype="float64")
-        var.units = unit
+        # the reference's unit strings are kept (bs.py:499: "1/(m·s)"); NetCDF-3 attributes are ASCII-only
+        var.units = unit if kind == "nc4" else unit.encode("ascii", "replace").decode("ascii").replace("?", ".")
     ds.close()
 
 
