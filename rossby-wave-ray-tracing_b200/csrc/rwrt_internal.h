@@ -14,6 +14,8 @@ void launch_rk45_setup_fast(const RunParams &p, int prepare_blocks, int fill_blo
 void launch_rk45_setup_strict(const RunParams &p, int prepare_blocks, int fill_blocks, cudaStream_t s, cudaStream_t aux);
 void launch_rk45_window_fast(const RunParams &p, int integrate_blocks, cudaStream_t s);
 void launch_rk45_window_strict(const RunParams &p, int integrate_blocks, cudaStream_t s);
+void launch_expand_records_fast(const RunParams &p, cudaStream_t s);
+void launch_expand_records_strict(const RunParams &p, cudaStream_t s);
 void launch_rk4_fast(const RunParams &p, cudaStream_t s);
 void launch_rk4_strict(const RunParams &p, cudaStream_t s);
 int occupancy_rk45_fast(bool coop);
@@ -51,7 +53,7 @@ void launch_grid_accumulate(long long nslot, int nt, const double *out7, double 
 int measure_fp64_peak(int sm_count, double *tflops, cudaStream_t s);
 
 // rwrt_api.cu helpers
-void launch_compact_live(long long N, int nt, const double *out7, int nsource, int nzwn, int32_t *live,
+void launch_compact_live(long long N, int nt, const double *out7, int nsource, int nzwn, int32_t *live, int32_t *inv,
                          unsigned long long *nlive_dev, int *block_counts, int nblocks, cudaStream_t s);
 
 }  // namespace rwrt

@@ -160,6 +160,65 @@ __global__ void __launch_bounds__(256) fill_static_slots(RunParams p)
     }
 }
 
+// Record layout, second half: rows [it_begin, it_end) of the reference layout from the per-ray records -- a
+// transpose through shared memory.  A block owns a tile of 32 consecutive slots x 16 rows: its warps read the
+// records of a ray 512 contiguous bytes at a time (8 rows x 64 B), and write, per (plane, row), 32 consecutive
+// slots = 256 contiguous bytes.  NaN-root slots get their constant rows, rows beyond a
+// ray's last valid row are NaN (wr.py:838-855).  This pass replaces the pre-fill: every output byte is written once.
+constexpr int EX_SLOTS = 32, EX_ROWS = 16, EX_STRIDE = EX_ROWS * 8 + 1;   // doubles per slot in the tile (odd: no conflicts)
+__global__ void __launch_bounds__(256) expand_records(RunParams p)
+{
+    __shared__ double tile[EX_SLOTS * EX_STRIDE];
+    const long long slot0 = (long long)blockIdx.x * EX_SLOTS;
+    const int row0 = p.it_begin + blockIdx.y * EX_ROWS;
+    const size_t pl = (size_t)p.nt * p.N;
+    const double n = qnan();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rr = lane >> 2, c = lane & 3;                                // row within a pass of 8, 16-byte piece of the record
+    // load phase: warp w fills slots 4w .. 4w+3 of the tile
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int s = 4 * warp + q;
+        const long long slot = slot0 + s;
+        if (slot >= p.N) break;
+        const int li = p.inv[slot];
+        double *t = tile + s * EX_STRIDE;
+        if (li < 0) {   // NaN-root slot: planes 0..4 keep their t = 0 value, ug / vg are NaN
+            double a = (2 * c < 5) ? p.out[(size_t)(2 * c) * pl + slot] : n;
+            double b = (2 * c + 1 < 5) ? p.out[(size_t)(2 * c + 1) * pl + slot] : n;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                t[(rr + 8 * h) * 8 + 2 * c] = a;
+                t[(rr + 8 * h) * 8 + 2 * c + 1] = b;
+            }
+            if (blockIdx.y == 0 && p.it_begin == 1 && lane == 0) {
+                if (p.accepted) p.accepted[slot] = 0;
+                if (p.attempts) p.attempts[slot] = 0;
+                if (p.status) p.status[slot] = 0;
+            }
+        } else {
+            const int rd = p.rows_done[li];
+            const double2 *rec = reinterpret_cast<const double2 *>(p.rec + ((size_t)li * p.rec_rows) * 8);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int it = row0 + rr + 8 * h;
+                double2 v = make_double2(n, n);
+                if (it < rd && it < p.it_end) v = __ldcs(rec + (size_t)(it - p.it_begin) * 4 + c);
+                t[(rr + 8 * h) * 8 + 2 * c] = v.x;
+                t[(rr + 8 * h) * 8 + 2 * c + 1] = v.y;
+            }
+        }
+    }
+    __syncthreads();
+    // store phase: (plane, row) pairs round-robin over the warps, 32 consecutive slots per store
+    const long long slot = slot0 + lane;
+    for (int pr = warp; pr < 7 * EX_ROWS; pr += 8) {
+        const int plane = pr % 7, r = pr / 7;
+        const int it = row0 + r;
+        if (it < p.it_end && slot < p.N) __stcs(p.out + (size_t)plane * pl + (size_t)it * p.N + slot, tile[lane * EX_STRIDE + r * 8 + plane]);
+    }
+}
+
 // Per-lane ray state kept in registers; the seven stage vectors K1..K7 live in shared memory
 // (ks[stage][component][thread], conflict-free), which keeps the kernel at <= 128 registers and
 // 16 resident warps per SM instead of 8.
@@ -860,7 +919,15 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                 ug = gv.x;
                 vg = gv.y;
             }
-            write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
+            if (p.rec) {  // record layout: 64 contiguous bytes per (ray, row), four 16-byte stores
+                double2 *r = reinterpret_cast<double2 *>(p.rec + ((size_t)my_ray * p.rec_rows + (L.it - p.it_begin)) * 8);
+                r[0] = make_double2(L.y[0], L.y[1]);
+                r[1] = make_double2(L.y[2], L.y[3]);
+                r[2] = make_double2(L.y[4], ug);
+                r[3] = make_double2(vg, 0.0);
+            } else {
+                write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
+            }
             L.plon = L.y[0];
             L.plat = L.y[1];
             pcos = masked ? cos(L.y[1]) : cos_new;
@@ -869,6 +936,7 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
         const bool finished = dead || L.it >= p.nt;
         if (finished || L.it >= p.it_end) {  // ray finished, or parked at the end of this time window
             double *st = p.state + (size_t)my_ray * RWRT_STATE;
+            if (p.rows_done) p.rows_done[my_ray] = L.it;                  // rows 0 .. L.it-1 of this ray are valid
             if (finished) {
                 if (p.accepted) p.accepted[L.slot] = L.acc;
                 if (p.attempts) p.attempts[L.slot] = L.att;

@@ -9,8 +9,14 @@ void launch_rk45_setup_fast(const RunParams &p, int prepare_blocks, int fill_blo
 {
     if (p.nlive > 0) fast::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
     // The constant rows of NaN-root slots touch no slot the integrator writes: low-priority side stream.
-    if (p.N > 0 && p.nt > 1)
+    if (p.N > 0 && p.nt > 1 && !p.rec)   // record layout: expand_records writes every row instead
         fast::fill_static_slots<<<dim3(fill_blocks, p.nt - 1 < 24 ? p.nt - 1 : 24), 256, 0, aux>>>(p);
+}
+void launch_expand_records_fast(const RunParams &p, cudaStream_t s)
+{
+    int rows = p.it_end - p.it_begin;
+    if (p.N > 0 && rows > 0)
+        fast::expand_records<<<dim3((unsigned)((p.N + fast::EX_SLOTS - 1) / fast::EX_SLOTS), (rows + fast::EX_ROWS - 1) / fast::EX_ROWS), 256, 0, s>>>(p);
 }
 
 // One time window [p.it_begin, p.it_end) of output rows for every live ray (the per-lane kernel has no

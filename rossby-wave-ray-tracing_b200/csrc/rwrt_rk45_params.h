@@ -17,6 +17,12 @@ struct RunParams {
     long long nlive;
     double *state;              // (nlive, RWRT_STATE): y[5], f[5], h_abs, cos(prev lat), t, prev lon, prev lat, counters
     int coop;                   // 1: cooperative-gather integrator (default); 0: per-lane gather (cross-check)
+    // optional record layout (RWRT_RECORDS=1): the integrator writes one 64-byte record per (ray, output row) and
+    // expand_records turns them into the reference layout afterwards (no partial-sector stores)
+    double *rec;                // (nlive, rec_rows, 8) or nullptr
+    int rec_rows;               // rows per ray in `rec` (= rows of the largest time window)
+    int32_t *rows_done;         // (nlive): number of valid rows 0..rows_done-1 of a ray so far
+    const int32_t *inv;         // (N): slot -> index in the live list, -1 for NaN-root slots
     int it_begin, it_end;       // this launch produces output rows [it_begin, it_end) (time window)
     long long *accepted;        // (N) or nullptr
     long long *attempts;        // (N) or nullptr

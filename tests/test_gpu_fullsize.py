@@ -136,7 +136,9 @@ def test_c2_full_size_properties(monkeypatch):
 
 def test_schedule_and_gather_independence(monkeypatch):
     """A quarter of C2 (287 k slots): the result may not depend on how rays are scheduled onto lanes (resident
-    blocks per SM, time windows) -- any stale or racing use of a warp's shared staging rows would show up here --
+    blocks per SM, time windows) nor on the output path (per-ray records + transpose, the default, or direct
+    stores into the reference layout after a pre-fill) -- any stale or racing use of a warp's shared staging rows
+    would show up here --
     and, in the strict build, the warp-cooperative gather must agree bit for bit with the per-lane gather kernel
     (two independent implementations of interpolation.py:103-135)."""
     nlon, nlat = 360, 181
@@ -151,7 +153,8 @@ def test_schedule_and_gather_independence(monkeypatch):
             ck, acc0 = _checksum(out), acc.clone()
             del out
             variants = [{"RWRT_BLOCKS_PER_SM": "1"}, {"RWRT_BLOCKS_PER_SM": "2"},
-                        {"RWRT_BLOCKS_PER_SM": "2", "RWRT_WINDOWS": "4"}, {"RWRT_WINDOWS": "9"}]
+                        {"RWRT_BLOCKS_PER_SM": "2", "RWRT_WINDOWS": "4"}, {"RWRT_WINDOWS": "9"},
+                        {"RWRT_RECORDS": "0"}, {"RWRT_RECORDS": "0", "RWRT_WINDOWS": "3"}]   # direct stores + pre-fill
             if flags == lib.MODE_STRICT:
                 variants.append({"RWRT_PER_LANE_GATHER": "1"})
             for env in variants:
