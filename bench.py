@@ -293,6 +293,8 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("RWRT_BENCH_VERBOSE") and rank == 0:
+        print("per-step kernel ms:", [round(k, 2) for k in kern_ms], file=sys.stderr)
     ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     s = torch.tensor([float(steps_done)], dtype=torch.float64, device=dev)

@@ -511,12 +511,15 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     if (nwin > nt - 1) nwin = nt - 1;
     if (use_records) {
         // the records of one time window must fit beside everything else: more windows when memory is short
-        size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
-        free_b += h->records.cap;                   // a buffer from an earlier call is reused
-        const size_t budget = free_b > (3ull << 30) ? free_b - (2ull << 30) : free_b / 2;
         const size_t per_row = (size_t)nlive * 8 * sizeof(double);
-        int max_rows = (int)(budget / per_row);
+        size_t budget = h->records.cap;             // a buffer from an earlier call is reused as it is ...
+        if (budget < per_row * (size_t)((nt - 1 + nwin - 1) / nwin + 1)) {   // ... unless it is too small (cudaMemGetInfo costs ms)
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            free_b += h->records.cap;
+            budget = free_b > (3ull << 30) ? free_b - (2ull << 30) : free_b / 2;
+        }
+        int max_rows = (int)(budget / per_row < 2147483647ull ? budget / per_row : 2147483647ull);
         if (max_rows < 2) return fail(RWRT_ERR_NOMEM, "no room for the ray records (%llu rays): shard the sources", nlive);
         int need_win = (nt - 1 + (max_rows - 1) - 1) / (max_rows - 1);
         if (need_win > nwin) nwin = need_win;

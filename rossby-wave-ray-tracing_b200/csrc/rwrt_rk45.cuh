@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(256) fill_static_slots(RunParams p)
 // records of a ray 512 contiguous bytes at a time (8 rows x 64 B), and write, per (plane, row), 32 consecutive
 // slots = 256 contiguous bytes.  NaN-root slots get their constant rows, rows beyond a
 // ray's last valid row are NaN (wr.py:838-855).  This pass replaces the pre-fill: every output byte is written once.
-constexpr int EX_SLOTS = 32, EX_ROWS = 16, EX_STRIDE = EX_ROWS * 8 + 1;   // doubles per slot in the tile (odd: no conflicts)
+#ifndef RWRT_EX_ROWS
+#define RWRT_EX_ROWS 16
+#endif
+constexpr int EX_SLOTS = 32, EX_ROWS = RWRT_EX_ROWS, EX_STRIDE = EX_ROWS * 8 + 1;   // doubles per slot in the tile (odd: no conflicts)
 __global__ void __launch_bounds__(256) expand_records(RunParams p)
 {
     __shared__ double tile[EX_SLOTS * EX_STRIDE];
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256) expand_records(RunParams p)
             double a = (2 * c < 5) ? p.out[(size_t)(2 * c) * pl + slot] : n;
             double b = (2 * c + 1 < 5) ? p.out[(size_t)(2 * c + 1) * pl + slot] : n;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < EX_ROWS / 8; ++h) {
                 t[(rr + 8 * h) * 8 + 2 * c] = a;
                 t[(rr + 8 * h) * 8 + 2 * c + 1] = b;
             }
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(256) expand_records(RunParams p)
             const int rd = p.rows_done[li];
             const double2 *rec = reinterpret_cast<const double2 *>(p.rec + ((size_t)li * p.rec_rows) * 8);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < EX_ROWS / 8; ++h) {
                 const int it = row0 + rr + 8 * h;
                 double2 v = make_double2(n, n);
                 if (it < rd && it < p.it_end) v = __ldcs(rec + (size_t)(it - p.it_begin) * 4 + c);
@@ -921,10 +924,17 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
             }
             if (p.rec) {  // record layout: 64 contiguous bytes per (ray, row), four 16-byte stores
                 double2 *r = reinterpret_cast<double2 *>(p.rec + ((size_t)my_ray * p.rec_rows + (L.it - p.it_begin)) * 8);
+#ifdef RWRT_REC_STCS
+                __stcs(r + 0, make_double2(L.y[0], L.y[1]));
+                __stcs(r + 1, make_double2(L.y[2], L.y[3]));
+                __stcs(r + 2, make_double2(L.y[4], ug));
+                __stcs(r + 3, make_double2(vg, 0.0));
+#else
                 r[0] = make_double2(L.y[0], L.y[1]);
                 r[1] = make_double2(L.y[2], L.y[3]);
                 r[2] = make_double2(L.y[4], ug);
                 r[3] = make_double2(vg, 0.0);
+#endif
             } else {
                 write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
             }
