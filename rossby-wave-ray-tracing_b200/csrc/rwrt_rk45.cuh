@@ -168,7 +168,11 @@ __global__ void __launch_bounds__(256) fill_static_slots(RunParams p)
 #ifndef RWRT_EX_ROWS
 #define RWRT_EX_ROWS 16
 #endif
-constexpr int EX_SLOTS = 32, EX_ROWS = RWRT_EX_ROWS, EX_STRIDE = EX_ROWS * 8 + 1;   // doubles per slot in the tile (odd: no conflicts)
+#ifndef RWRT_EX_SLOTS
+#define RWRT_EX_SLOTS 32
+#endif
+constexpr int EX_SLOTS = RWRT_EX_SLOTS, EX_ROWS = RWRT_EX_ROWS, EX_STRIDE = EX_ROWS * 8 + 1;   // doubles per slot in the tile (odd: no conflicts)
+static_assert(EX_SLOTS % 32 == 0 && EX_ROWS % 8 == 0 && EX_SLOTS * EX_STRIDE * 8 <= 48 * 1024, "expand_records tile");
 __global__ void __launch_bounds__(256) expand_records(RunParams p)
 {
     __shared__ double tile[EX_SLOTS * EX_STRIDE];
@@ -178,10 +182,10 @@ __global__ void __launch_bounds__(256) expand_records(RunParams p)
     const double n = qnan();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = lane >> 2, c = lane & 3;                                // row within a pass of 8, 16-byte piece of the record
-    // load phase: warp w fills slots 4w .. 4w+3 of the tile
+    // load phase: warp w fills slots w, w + 8, ... of the tile
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int s = 4 * warp + q;
+    for (int q = 0; q < EX_SLOTS / 8; ++q) {
+        const int s = warp + 8 * q;
         const long long slot = slot0 + s;
         if (slot >= p.N) break;
         const int li = p.inv[slot];
@@ -213,12 +217,21 @@ __global__ void __launch_bounds__(256) expand_records(RunParams p)
         }
     }
     __syncthreads();
-    // store phase: (plane, row) pairs round-robin over the warps, 32 consecutive slots per store
-    const long long slot = slot0 + lane;
-    for (int pr = warp; pr < 7 * EX_ROWS; pr += 8) {
-        const int plane = pr % 7, r = pr / 7;
-        const int it = row0 + r;
-        if (it < p.it_end && slot < p.N) __stcs(p.out + (size_t)plane * pl + (size_t)it * p.N + slot, tile[lane * EX_STRIDE + r * 8 + plane]);
+    // store phase: warp w writes rows w, w + 8, ... of all seven planes; per (plane, row) EX_SLOTS consecutive
+    // slots = 512 contiguous bytes, in back-to-back 256-byte stores
+#pragma unroll
+    for (int j = 0; j < EX_ROWS / 8; ++j) {
+        const int r = warp + 8 * j, it = row0 + r;
+        if (it >= p.it_end) break;
+#pragma unroll
+        for (int plane = 0; plane < 7; ++plane) {
+#pragma unroll
+            for (int half = 0; half < EX_SLOTS / 32; ++half) {
+                const long long slot = slot0 + 32 * half + lane;
+                if (slot < p.N)
+                    __stcs(p.out + (size_t)plane * pl + (size_t)it * p.N + slot, tile[(32 * half + lane) * EX_STRIDE + r * 8 + plane]);
+            }
+        }
     }
 }
 
@@ -924,17 +937,10 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
             }
             if (p.rec) {  // record layout: 64 contiguous bytes per (ray, row), four 16-byte stores
                 double2 *r = reinterpret_cast<double2 *>(p.rec + ((size_t)my_ray * p.rec_rows + (L.it - p.it_begin)) * 8);
-#ifdef RWRT_REC_STCS
-                __stcs(r + 0, make_double2(L.y[0], L.y[1]));
-                __stcs(r + 1, make_double2(L.y[2], L.y[3]));
-                __stcs(r + 2, make_double2(L.y[4], ug));
-                __stcs(r + 3, make_double2(vg, 0.0));
-#else
                 r[0] = make_double2(L.y[0], L.y[1]);
                 r[1] = make_double2(L.y[2], L.y[3]);
                 r[2] = make_double2(L.y[4], ug);
-                r[3] = make_double2(vg, 0.0);
-#endif
+                r[3] = make_double2(vg, 0.0);   // plain stores: streaming (.cs) ones measured the same
             } else {
                 write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
             }
