@@ -337,7 +337,7 @@ def run_ours(a):
             "unit": "TFLOP/s", "frac": achieved_tf / (peak_tf.value or NOMINAL_FP64_TFLOPS),
             "peak_source": "measured DFMA-chain microbenchmark in this run (rwrt_measure_fp64_peak); nominal 37.2",
             "flop_per_step": FLOP_PER_STEP, "kernel_ms": kms, "traffic": traffic,
-            "kernel": "rk45_integrate_coop (+ rk45_prepare, fill_static_slots inside the same event pair)",
+            "kernel": "rk45_integrate_coop (+ rk45_prepare and the expand_records transpose inside the same event pair)",
             "hbm": {"achieved": hbm_alg / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_alg / (kms * 1e-3) / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}

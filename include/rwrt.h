@@ -166,6 +166,10 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
                      double cut_off, uint32_t flags, double *out7_host, int64_t *accepted_host,
                      int8_t *status_host, int64_t *total_accepted_host, void *stream);
 
+/* Releases the handle's scratch memory (ray records -- 64 B per live ray and output row of a time window --, ray
+ * state, work lists).  The next run allocates again.  The fields stay. */
+int rwrt_trim(rwrt_handle h);
+
 /* counters of the last rwrt_ray_run_rk45 on this handle (host side, after a sync):
  * [0] kernels launched, [1] live rays, [2] ms of the integrate kernel(s) by CUDA events */
 int rwrt_last_run_stats(rwrt_handle h, double *stats3);

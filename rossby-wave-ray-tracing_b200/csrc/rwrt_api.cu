@@ -582,6 +582,20 @@ int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int
                     accepted, attempts, status, total_accepted, stream, nwin, nullptr, nullptr);
 }
 
+int rwrt_trim(rwrt_handle h)
+{
+    if (!h) return fail(RWRT_ERR_ARG, "rwrt_trim: null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    h->records.release();
+    h->rows_done.release();
+    h->inv.release();
+    h->state.release();
+    h->live.release();
+    h->blockcnt.release();
+    return RWRT_OK;
+}
+
 int rwrt_last_run_stats(rwrt_handle h, double *stats3)
 {
     if (!h || !stats3) return fail(RWRT_ERR_ARG, "rwrt_last_run_stats: NULL argument");

@@ -498,16 +498,17 @@ constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE;                         // pe
 constexpr int CO_LIST_OFS = 384, CO_LIST_STRIDE = CO_REC_STRIDE;           // fetch-list entry j sits in the pad of row j
 
 // Stage vectors K2..K6 (25 doubles per ray) live in TENSOR MEMORY: lane = thread, 10 x 32-bit columns per
-// stage vector, 64 columns per block.  That takes 6.25 KB per warp out of shared memory, which was what
-// capped residency at 12 warps per SM; with TMEM the kernel runs 4 blocks = 16 warps per SM (and fits 128
-// registers).  No tensor-core instruction is involved -- tcgen05.ld / .st with the 32x32b shape give every
-// thread a private 32-bit x ncol scratch row.  RWRT_TMEM_KS=1 selects it; measured slower than the shared-memory layout at 12 warps, so off by default.
+// stage vector, 64 columns per block.  No tensor-core instruction is involved -- tcgen05.ld / .st with the 32x32b
+// shape give every thread a private 32-bit x ncol scratch row.  This takes ~45 LDS/STS wavefronts per stage off the
+// shared-memory pipe, which is the busiest unit of this kernel (84 % with K2..K6 in shared memory, profiles/r1_v14):
+// 56.9 -> 54.1 ms per C2 pass at the same 12 warps per SM.  Using the freed shared memory for a fourth block per SM
+// (16 warps at 128 registers) is slower (57.7 ms): RWRT_CO_BLOCKS stays 3.  RWRT_TMEM_KS=0 keeps K2..K6 in shared memory.
 #ifndef RWRT_TMEM_KS
-#define RWRT_TMEM_KS 0
+#define RWRT_TMEM_KS 1
 #endif
 constexpr int CO_TMEM_COLS = 64;     // power of two >= 50
 #ifndef RWRT_CO_BLOCKS
-#define RWRT_CO_BLOCKS 4
+#define RWRT_CO_BLOCKS 3
 #endif
 #if RWRT_TMEM_KS
 constexpr int CO_BLOCKS_PER_SM = RWRT_CO_BLOCKS;

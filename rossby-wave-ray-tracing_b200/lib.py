@@ -19,7 +19,7 @@ RAY_NO_ROOT, RAY_ALIVE, RAY_POLE, RAY_SPEED, RAY_NAN = 0, 1, 2, 3, 4
 # every symbol include/rwrt.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = (
     "rwrt_abi_version", "rwrt_last_error", "rwrt_device_count", "rwrt_host_alloc", "rwrt_host_free",
-    "rwrt_create", "rwrt_destroy", "rwrt_bs_ready", "rwrt_bs_set_fields", "rwrt_sample_mercator", "rwrt_sample_mercator18", "rwrt_rhs",
+    "rwrt_create", "rwrt_destroy", "rwrt_trim", "rwrt_bs_ready", "rwrt_bs_set_fields", "rwrt_sample_mercator", "rwrt_sample_mercator18", "rwrt_rhs",
     "rwrt_ray_init", "rwrt_ray_run_rk45", "rwrt_ray_run_rk45_d2h", "rwrt_ray_run_rk4", "rwrt_grid_accumulate", "rwrt_real2d_host", "rwrt_last_run_stats", "rwrt_measure_fp64_peak",
     "rwrt_shsf_plan_create", "rwrt_shsf_out_shape", "rwrt_shsf_apply", "rwrt_shsf_plan_destroy",
 )
@@ -50,6 +50,7 @@ def load():
     L.rwrt_host_free.argtypes = [vp]
     L.rwrt_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
     L.rwrt_destroy.argtypes = [vp]
+    L.rwrt_trim.argtypes = [vp]
     L.rwrt_bs_ready.argtypes = [vp] + [vp] * 8 + [vp]
     L.rwrt_bs_set_fields.argtypes = [vp, vp, vp, vp, vp]
     L.rwrt_sample_mercator.argtypes = [vp, i64, vp, vp, vp, vp, vp]
