@@ -880,7 +880,9 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
         double r[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {  // rkf45.py:442-446
-            double scale = p.atol + np_maximum(fabs(L.y[c]), fabs(ys[c])) * p.rtol;
+            // np.maximum propagates NaN (rkf45.py:443); in the fast build plain fmax is enough: whenever y_new[c] is
+            // NaN so is e[c] (the sum keeps its zero-coefficient terms), and the quotient below is NaN either way
+            double scale = p.atol + (RWRT_FAST ? fmax(fabs(L.y[c]), fabs(ys[c])) : np_maximum(fabs(L.y[c]), fabs(ys[c]))) * p.rtol;
             const double e = ee[c];
             r[c] = RWRT_FAST ? (h * e) * rcp_fast(scale) : (h * e) / scale;   // scale >= atol > 0, never denormal
         }
