@@ -256,15 +256,6 @@ __device__ __forceinline__ void write_row(const RunParams &p, long long slot, in
 {
     const size_t pl = (size_t)p.nt * p.N;
     size_t o = (size_t)it * p.N + slot;
-#if RWRT_STCS
-    __stcs(p.out + 0 * pl + o, lon);
-    __stcs(p.out + 1 * pl + o, lat);
-    __stcs(p.out + 2 * pl + o, k);
-    __stcs(p.out + 3 * pl + o, l);
-    __stcs(p.out + 4 * pl + o, a);
-    __stcs(p.out + 5 * pl + o, ug);
-    __stcs(p.out + 6 * pl + o, vg);
-#else
     p.out[0 * pl + o] = lon;
     p.out[1 * pl + o] = lat;
     p.out[2 * pl + o] = k;
@@ -272,7 +263,6 @@ __device__ __forceinline__ void write_row(const RunParams &p, long long slot, in
     p.out[4 * pl + o] = a;
     p.out[5 * pl + o] = ug;
     p.out[6 * pl + o] = vg;
-#endif
 }
 
 // rkf45.py:453-455 / 474-475: 0.9 * err^-0.2 clipped to [0.2, 10].  The clip makes pow() unnecessary
@@ -489,9 +479,6 @@ __global__ void __launch_bounds__(RK_THREADS, 4) rk45_integrate(RunParams p)
 // latitude neighbours are contiguous).  v4-v11 read one 384-byte record of a cell-major COPY of the table instead:
 // same number of 16-byte copies per ray and the same speed at 1 degree, but the copy was 4x the size (399 MB at
 // 0.25 degree, 25 GB for a 1000-member ensemble) and those configurations fell back to the per-lane kernel.
-#ifndef RWRT_BENIGN_POS
-#define RWRT_BENIGN_POS(c) 0.0   /* (lon, lat) of the state idle lanes run along on */
-#endif
 constexpr int CO_REC_STRIDE = 400;   // 25 x 16 B per staged ray (4 points x 96 B + 16 B holding the fetch-list entry):
                                      // an odd number of 16-byte chunks, so a quarter-warp's LDS.128 / LDGSTS never conflict
 constexpr int CO_STAGE_BYTES = 32 * CO_REC_STRIDE;                         // per warp; 4 warps + K2..K6 = 76 800 B = 3 blocks / SM exactly
@@ -578,9 +565,6 @@ __device__ __forceinline__ void tm_combo(unsigned tk, const double *k1, const do
 #ifndef RWRT_L2_HINT
 #define RWRT_L2_HINT 1
 #endif
-#ifndef RWRT_STCS
-#define RWRT_STCS 0
-#endif
 __device__ __forceinline__ unsigned long long l2_policy_evict_last()
 {
     unsigned long long pol;
@@ -627,7 +611,7 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     L.slot = -1;
     double k1[5] = {0, 0, 0, 0, 0};
 #pragma unroll
-    for (int c = 0; c < 5; ++c) L.y[c] = (c < 2) ? RWRT_BENIGN_POS(c) : 1.0;              // benign state for idle lanes
+    for (int c = 0; c < 5; ++c) L.y[c] = (c < 2) ? 0.0 : 1.0;              // benign state for idle lanes
     L.h_abs = 1.0;
     L.t = 0.0;
     const double *fb = p.g.fpk;
@@ -979,7 +963,7 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
             L.slot = -1;
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
-                L.y[c] = (c < 2) ? RWRT_BENIGN_POS(c) : 1.0;
+                L.y[c] = (c < 2) ? 0.0 : 1.0;
                 k1[c] = 0.0;
             }
             L.h_abs = 1.0;
