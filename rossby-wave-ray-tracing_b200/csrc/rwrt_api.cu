@@ -687,6 +687,11 @@ int rwrt_ray_run_rk4(rwrt_handle h, int nsource, const int32_t *src_member, int 
     p.cut = cut_off * tstep / 3600.;  // wr.py:170
     p.out = out7;
     p.status = (signed char *)status;
+    // fast build: cooperative-gather kernel with FSAL (40.7 ms per C2 pass against 56.5); strict build: the per-lane
+    // kernel (143 ms against 156: libdevice trigonometry dominates there).  RWRT_PER_LANE_GATHER=0 / 1 forces one.
+    p.coop = (flags & RWRT_MODE_STRICT) ? 0 : 1;
+    if (const char *e = getenv("RWRT_PER_LANE_GATHER")) p.coop = (atoi(e) == 0);
+    if ((long long)h->nmember * h->nlon_f * h->nlat >= (1LL << 30) - 1) p.coop = 0;
     if (flags & RWRT_MODE_STRICT) launch_rk4_strict(p, (cudaStream_t)stream);
     else launch_rk4_fast(p, (cudaStream_t)stream);
     CU(cudaGetLastError());

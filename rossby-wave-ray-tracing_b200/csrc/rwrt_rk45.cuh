@@ -580,6 +580,45 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src, u
 #endif
 }
 
+// Warp-cooperative request for the four corner points of every lane's cell (used by rk45_integrate_coop and
+// rk4_integrate_coop; expects the kernels' local names: p, FULL, lane_id, grp, q8, member_pt, prev_key, fetch_list,
+// pf_src / pf_dx / pf_dy / pf_dst, l2pol and the outputs inr, x0, y0, x1, y1, sx, sy).
+#define RWRT_FETCH(LON, LAT)                                                                                         \
+    {                                                                                                                \
+        inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
+        locate<RWRT_FAST>(p.g, LON, inr ? (LAT) : 0.0, x0, y0, x1, y1, sx, sy);                                      \
+        /* what gets staged = point (x0, y0) AND the clamp pattern (interpolation.py:116-119: x1, y1 come from the   \
+           UNCLAMPED index, so a NaN / out-of-range position can pair (x0, y0) with x1 == x0); both are in the key: \
+           bits 0..29 point index in the table (all members), bit 30 x clamped, bit 31 y clamped */                  \
+        const unsigned key = (member_pt + (unsigned)(x0 * p.g.nlat + y0)) | (x1 == x0 ? 0x40000000u : 0u) |          \
+                             (y1 == y0 ? 0x80000000u : 0u);                                                          \
+        /* a ray often stays in its cell from one stage to the next: its corners are still staged, no new copy */   \
+        const bool need = (key != prev_key);                                                                         \
+        const unsigned need_mask = __ballot_sync(FULL, need);                                                        \
+        prev_key = key;                                                                                              \
+        /* compact list of the cells to fetch: (key, destination lane) */                                            \
+        if (need)                                                                                                    \
+            *reinterpret_cast<uint2 *>(fetch_list + __popc(need_mask & ((1u << lane_id) - 1u)) * CO_LIST_STRIDE) =   \
+                make_uint2(key, (unsigned)lane_id * CO_REC_STRIDE);                                                  \
+        __syncwarp();                                                                                                \
+        const int nfetch = __popc(need_mask);                                                                        \
+        /* quarter-warp `grp` copies list entries grp, grp+4, ...: lane q8 moves 16-byte half (q8 & 1) of the three  \
+           sectors of corner q8 >> 1 -- 24 x 16 B per cell */                                                        \
+        for (int j = grp; j < nfetch; j += 4) {                                                                      \
+            const uint2 e = *reinterpret_cast<const uint2 *>(fetch_list + j * CO_LIST_STRIDE);                       \
+            const char *sp = pf_src + (size_t)(e.x & 0x3fffffffu) * (NPK * 8);                                       \
+            if (e.x >> 30) {                                                /* clamped: the far corner is the near one */ \
+                if (e.x & 0x40000000u) sp -= pf_dx;                                                                  \
+                if (e.x & 0x80000000u) sp -= pf_dy;                                                                  \
+            }                                                                                                        \
+            const unsigned dst = pf_dst + e.y;                                                                       \
+            cp_async16(dst, sp, l2pol);                                                                              \
+            cp_async16(dst + 32, sp + 32, l2pol);                                                                    \
+            cp_async16(dst + 64, sp + 64, l2pol);                                                                    \
+        }                                                                                                            \
+        asm volatile("cp.async.commit_group;\n" ::);                                                                 \
+    }
+
 __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_coop(RunParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -697,41 +736,6 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
         int x0, y0, x1, y1;
         double sx, sy;
         bool inr;
-#define RWRT_FETCH(LON, LAT)                                                                                         \
-    {                                                                                                                \
-        inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
-        locate<RWRT_FAST>(p.g, LON, inr ? (LAT) : 0.0, x0, y0, x1, y1, sx, sy);                                      \
-        /* what gets staged = point (x0, y0) AND the clamp pattern (interpolation.py:116-119: x1, y1 come from the   \
-           UNCLAMPED index, so a NaN / out-of-range position can pair (x0, y0) with x1 == x0); both are in the key: \
-           bits 0..29 point index in the table (all members), bit 30 x clamped, bit 31 y clamped */                  \
-        const unsigned key = (member_pt + (unsigned)(x0 * p.g.nlat + y0)) | (x1 == x0 ? 0x40000000u : 0u) |          \
-                             (y1 == y0 ? 0x80000000u : 0u);                                                          \
-        /* a ray often stays in its cell from one stage to the next: its corners are still staged, no new copy */   \
-        const bool need = (key != prev_key);                                                                         \
-        const unsigned need_mask = __ballot_sync(FULL, need);                                                        \
-        prev_key = key;                                                                                              \
-        /* compact list of the cells to fetch: (key, destination lane) */                                            \
-        if (need)                                                                                                    \
-            *reinterpret_cast<uint2 *>(fetch_list + __popc(need_mask & ((1u << lane_id) - 1u)) * CO_LIST_STRIDE) =   \
-                make_uint2(key, (unsigned)lane_id * CO_REC_STRIDE);                                                  \
-        __syncwarp();                                                                                                \
-        const int nfetch = __popc(need_mask);                                                                        \
-        /* quarter-warp `grp` copies list entries grp, grp+4, ...: lane q8 moves 16-byte half (q8 & 1) of the three  \
-           sectors of corner q8 >> 1 -- 24 x 16 B per cell */                                                        \
-        for (int j = grp; j < nfetch; j += 4) {                                                                      \
-            const uint2 e = *reinterpret_cast<const uint2 *>(fetch_list + j * CO_LIST_STRIDE);                       \
-            const char *sp = pf_src + (size_t)(e.x & 0x3fffffffu) * (NPK * 8);                                       \
-            if (e.x >> 30) {                                                /* clamped: the far corner is the near one */ \
-                if (e.x & 0x40000000u) sp -= pf_dx;                                                                  \
-                if (e.x & 0x80000000u) sp -= pf_dy;                                                                  \
-            }                                                                                                        \
-            const unsigned dst = pf_dst + e.y;                                                                       \
-            cp_async16(dst, sp, l2pol);                                                                              \
-            cp_async16(dst + 32, sp + 32, l2pol);                                                                    \
-            cp_async16(dst + 64, sp + 64, l2pol);                                                                    \
-        }                                                                                                            \
-        asm volatile("cp.async.commit_group;\n" ::);                                                                 \
-    }
         // stage 1 input (rkf45.py:306-311): y + (K_1 a_21) h
 #pragma unroll
         for (int c = 0; c < 5; ++c) ys[c] = L.y[c] + (k1[c] * cC[1][0]) * h;
@@ -841,7 +845,6 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
             }
         }
 #undef RWRT_NEXT
-#undef RWRT_FETCH
         // now ys = y_new and kn = f(y_new) (rkf45.py:317-319); error estimate sum_s K_s E_s (rkf45.py:442-446)
         double ee[5];
 #if RWRT_TMEM_KS
@@ -1045,6 +1048,146 @@ __global__ void __launch_bounds__(128) rk4_integrate(RunParams p)
     }
     if (p.status) p.status[slot] = (signed char)code;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-step RK4 on the cooperative-gather machinery (the product path of rwrt_ray_run_rk4; rk4_integrate above is
+// kept as the cross-check).  Same arithmetic as rk4_integrate, two structural differences:
+//   * FSAL: the evaluation at y_new that the output needs (ug, vg; wr.py:737-746) is also the next step's k1
+//     (wr.py:598 recomputes the same value) -- 4 right-hand sides per step instead of 5;
+//   * the four corner points of each evaluation arrive through the warp's shared staging rows, requested one
+//     evaluation ahead (as in rk45_integrate_coop).
+// One slot per thread, all slots in lock step: rows are written fully coalesced in the reference layout.
+// ---------------------------------------------------------------------------------------------
+constexpr int RK4_SMEM_BYTES = (RK_THREADS / 32) * CO_STAGE_BYTES;
+__global__ void __launch_bounds__(RK_THREADS, 3) rk4_integrate_coop(RunParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x;
+    const int lane_id = tid & 31, warp_id = tid >> 5;
+    unsigned char *stage = smem_raw + warp_id * CO_STAGE_BYTES;
+    const unsigned stage_u32 = (unsigned)__cvta_generic_to_shared(stage);
+    const int q8 = lane_id & 7, grp = lane_id >> 3;
+    const unsigned char *my_rec = stage + lane_id * CO_REC_STRIDE;
+    const unsigned long long l2pol = l2_policy_evict_last();
+    unsigned char *fetch_list = stage + CO_LIST_OFS;
+    const unsigned pf_dst = stage_u32 + (unsigned)((q8 >> 1) * 96 + (q8 & 1) * 16);
+    const unsigned pf_dx = (q8 & 4) ? (unsigned)p.g.nlat * NPK * 8 : 0u;
+    const unsigned pf_dy = (q8 & 2) ? NPK * 8u : 0u;
+    const char *pf_src = reinterpret_cast<const char *>(p.g.fpk) + (q8 & 1) * 16 + pf_dx + pf_dy;
+    unsigned prev_key = 0xffffffffu;
+
+    long long slot = (long long)blockIdx.x * blockDim.x + tid;
+    const bool mine = slot < p.N;
+    if (!mine) slot = p.N - 1;                     // the warp works together: surplus lanes shadow the last slot, write nothing
+    const size_t pl = (size_t)p.nt * p.N;
+    const double *fb = member_base(p, slot);
+    const unsigned member_pt = (unsigned)((fb - p.g.fpk) / NPK);
+    double y[5], acc[5], kn[5], ys[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) ys[c] = y[c] = p.out[c * pl + slot];
+    double plon = y[0], plat = y[1];
+    const double dt = p.tstep;
+    int code = (y[3] == y[3]) ? 1 : 0;
+    int x0, y0, x1, y1;
+    double sx, sy, ug = 0, vg = 0;
+    bool inr, m_first = false, m_any = false;
+    // evaluation e of step it: e = 0 -> f(y) (only before the first step; afterwards FSAL), 1..3 -> k2..k4, 4 -> f(y_new)
+    RWRT_FETCH(ys[0], ys[1])
+    int e = 0, it = 0;
+    for (;;) {
+        const double lat = ys[1];
+        const double wa = (1 - sx) * sy, wb = sx * sy, wc = (1 - sx) * (1 - sy), wd = sx * (1 - sy);
+        const bool err = (fabs(lat) >= HALFPI) || (fabs(ys[3]) >= 100.0);   // wr.py:508-510
+        const Trig tg = trig_of_lat<RWRT_FAST>(inr ? lat : 0.0);
+        double yp[5] = {ys[0], ys[1], ys[2], (err || !inr) ? qnan() : ys[3], ys[4]};
+        WaveRecip wr;
+        if (RWRT_FAST) wr = wave_recip(yp[2], yp[3]);
+        double wa_ = wa, wd_ = wd, tcp = tg.cp, ttl = tg.tl, wkap = RWRT_FAST ? wr.kap : 0.0, wrden = RWRT_FAST ? wr.rden : 0.0;
+        asm volatile("" : "+d"(wa_), "+d"(wd_), "+d"(tcp), "+d"(ttl), "+d"(wkap), "+d"(wrden));
+        if (p.nt > 1) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+        Trig tgp = tg;
+        tgp.cp = tcp;
+        tgp.tl = ttl;
+        if (RWRT_FAST) {
+            wr.kap = wkap;
+            wr.rden = wrden;
+        }
+        double f[12];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double2 c2 = *reinterpret_cast<const double2 *>(my_rec + k * 16);
+            const double2 a2 = *reinterpret_cast<const double2 *>(my_rec + 96 + k * 16);
+            const double2 d2 = *reinterpret_cast<const double2 *>(my_rec + 192 + k * 16);
+            const double2 b2 = *reinterpret_cast<const double2 *>(my_rec + 288 + k * 16);
+            f[2 * k] = a2.x * wa_ + b2.x * wb + c2.x * wc + d2.x * wd_;
+            if (2 * k + 1 < 11) f[2 * k + 1] = a2.y * wa_ + b2.y * wb + c2.y * wc + d2.y * wd_;
+        }
+        Merc m = mercator_from_fields<RWRT_FAST>(f, tgp);
+        rhs_position<RWRT_FAST>(m, yp, wr, kn, ug, vg);
+        rhs_wavenumber<RWRT_FAST>(m, yp, wr, kn);
+        // ---- what this evaluation was, and where the next one is ----
+        bool done = false;
+        if (e == 0 || e == 4) {                     // kn = f(y): k1 of the coming step (wr.py:598)
+            if (e == 4) {                           // ... and the output of the step that just ended (wr.py:737-746)
+                if (err) {
+                    double2 gv = output_ugvg_slow(p.g, fb, y[0], y[1], y[2], y[3]);
+                    ug = gv.x;
+                    vg = gv.y;
+                }
+                if (mine) write_row(p, slot, it + 1, y[0], y[1], y[2], y[3], y[4], ug, vg);
+                plon = y[0];
+                plat = y[1];
+                ++it;
+                done = it >= p.nt - 1;
+            }
+            m_first = err;
+            m_any = false;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                acc[c] = kn[c];
+                ys[c] = y[c] + 0.5 * dt * kn[c];
+            }
+            e = 1;
+        } else if (e == 1 || e == 2) {              // k2, k3
+            m_any |= err;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                acc[c] = acc[c] + 2 * kn[c];
+                ys[c] = (e == 1) ? y[c] + 0.5 * dt * kn[c] : y[c] + dt * kn[c];
+            }
+            ++e;
+        } else {                                    // k4: finish the step (wr.py:598-618, 721-734)
+            m_any |= err;
+            if (!m_first && !m_any) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) y[c] = y[c] + (dt / 6.0) * (acc[c] + kn[c]);
+            }
+            if (fabs(y[1]) >= HALFPI) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) y[c] = qnan();
+                if (code == 1) code = 2;
+            }
+            double dd = haversine(y[0], y[1], plon, plat);
+            if (fabs(dd) >= p.cut) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) y[c] = qnan();
+                if (code == 1) code = 3;
+            }
+            if (code == 1 && !(y[0] + y[1] + y[2] + y[3] + y[4] == y[0] + y[1] + y[2] + y[3] + y[4])) code = 4;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) ys[c] = y[c];
+            e = 4;
+        }
+        if (done) break;
+        __syncwarp();                               // every lane has read its staged points
+        RWRT_FETCH(ys[0], ys[1])
+    }
+    if (mine && p.status) p.status[slot] = (signed char)code;
+}
+
+#undef RWRT_FETCH
 
 }  // namespace RWRT_VARIANT
 }  // namespace rwrt

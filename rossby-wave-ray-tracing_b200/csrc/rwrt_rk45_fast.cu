@@ -31,7 +31,13 @@ void launch_rk45_window_fast(const RunParams &p, int integrate_blocks, cudaStrea
 }
 void launch_rk4_fast(const RunParams &p, cudaStream_t s)
 {
-    if (p.N > 0 && p.nt > 1) fast::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+    if (p.N <= 0 || p.nt <= 1) return;
+    if (p.coop) {
+        cudaFuncSetAttribute(fast::rk4_integrate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RK4_SMEM_BYTES);
+        fast::rk4_integrate_coop<<<(unsigned)((p.N + 127) / 128), fast::RK_THREADS, fast::RK4_SMEM_BYTES, s>>>(p);
+    } else {
+        fast::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+    }
 }
 
 int occupancy_rk45_fast(bool coop)

@@ -31,7 +31,13 @@ void launch_rk45_window_strict(const RunParams &p, int integrate_blocks, cudaStr
 }
 void launch_rk4_strict(const RunParams &p, cudaStream_t s)
 {
-    if (p.N > 0 && p.nt > 1) strict::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+    if (p.N <= 0 || p.nt <= 1) return;
+    if (p.coop) {
+        cudaFuncSetAttribute(strict::rk4_integrate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::RK4_SMEM_BYTES);
+        strict::rk4_integrate_coop<<<(unsigned)((p.N + 127) / 128), strict::RK_THREADS, strict::RK4_SMEM_BYTES, s>>>(p);
+    } else {
+        strict::rk4_integrate<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+    }
 }
 
 int occupancy_rk45_strict(bool coop)
