@@ -412,9 +412,17 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    return {"value": float(s.item()) / float(t.item()), "unit": "steps/s", "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(t.item()) / reps,
-            "api": "rwrt_real2d_host (C ABI, host pointers; pinned result arrays)"}
+    import ctypes as C
+    hs = (C.c_double * 4)()
+    lib.check(L.rwrt_last_host_stats(h, hs), "rwrt_last_host_stats")   # bytes the library actually moved in the last call
+    if hs[3] > 0:
+        how = (f"ray records cross the link in {int(hs[2])} time windows, {int(hs[3])} host threads write the "
+               f"{nbytes/1e9:.1f} GB of result planes")
+    else:
+        how = f"device-expanded rows cross the link in {int(hs[2])} time windows"
+    return {"value": float(s.item()) / float(t.item()), "unit": "steps/s", "h2d_bytes_per_step": int(hs[1]),
+            "d2h_bytes_per_step": int(hs[0]), "result_bytes_per_step": d2h, "ms_per_step": 1e3 * float(t.item()) / reps,
+            "api": "rwrt_real2d_host (C ABI, host pointers; pinned inputs and result arrays)", "transfer": how}
 
 
 def main():

@@ -155,9 +155,14 @@ int rwrt_grid_accumulate(rwrt_handle h, int64_t nslot, int nt, const double *out
 
 /*
  * Whole ray path with HOST buffers (the call main_wr.real2d_hnf makes, main_wr.py:66-89, minus
- * NetCDF): H2D of u, v, coordinates, sources; BS.ready; ray_initial; RK45; D2H of the seven
- * result arrays (pinned memory from rwrt_host_alloc makes the copy-back asynchronous and
- * chunk-overlapped with the integration).  Synchronises before returning.
+ * NetCDF): H2D of u, v, coordinates, sources; BS.ready; ray_initial; RK45; the seven result arrays
+ * (wr.py:767-781) in out7_host.  Synchronises before returning.
+ * The integration runs in time windows.  Default: the 64-byte ray records of a finished window travel to pinned
+ * staging buffers kept on the handle while the next window integrates, and host threads (RWRT_HOST_THREADS,
+ * default: all cores) write the caller's planes from them -- about half of the reference-layout bytes are NaN /
+ * constant rows that never need to cross the link, and out7_host may be pageable.  RWRT_HOST_EXPAND=0: the device
+ * expands the records and the reference-layout rows travel (fast only into pinned memory, rwrt_host_alloc).
+ * Both forms give the same bits.
  */
 int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
                      const double *coslat, const double *sinlat, int nsource, const double *src_lon,
@@ -166,13 +171,29 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
                      double cut_off, uint32_t flags, double *out7_host, int64_t *accepted_host,
                      int8_t *status_host, int64_t *total_accepted_host, void *stream);
 
+/*
+ * Host half of rwrt_real2d_host on its own (pure host code, no device needed): writes rows [row_begin, row_end) of
+ * slots [slot_begin, slot_end) of the seven planes out7_host (7, nt, nslot) from the ray records of one time window.
+ * records: [ray][rec_rows][8] doubles = (lon, lat, k, l, A, u_g, v_g, pad) for rows row_begin ...; slot_to_ray[slot]
+ * = index of the slot's ray, < 0 for a slot without a real root (its planes 0..4 repeat row 0 of out7_host, u_g and
+ * v_g are NaN: wr.py:768-781 and SURVEY appendix C-7); rows >= rows_done[ray] are NaN in all planes (wr.py:838-855).
+ * row_begin >= 1 (row 0 is the t = 0 state and must already be in out7_host), row_end - row_begin <= rec_rows.
+ */
+int rwrt_host_expand_rows(double *out7_host, int nt, int64_t nslot, const int32_t *slot_to_ray, const double *records,
+                          const int32_t *rows_done, int rec_rows, int row_begin, int row_end, int64_t slot_begin,
+                          int64_t slot_end);
+
 /* Releases the handle's scratch memory (ray records -- 64 B per live ray and output row of a time window --, ray
- * state, work lists).  The next run allocates again.  The fields stay. */
+ * state, work lists, pinned staging buffers of rwrt_real2d_host).  The next run allocates again.  The fields stay. */
 int rwrt_trim(rwrt_handle h);
 
 /* counters of the last rwrt_ray_run_rk45 on this handle (host side, after a sync):
  * [0] kernels launched, [1] live rays, [2] ms of the integrate kernel(s) by CUDA events */
 int rwrt_last_run_stats(rwrt_handle h, double *stats3);
+
+/* the last rwrt_real2d_host on this handle: [0] bytes copied device -> host, [1] bytes host -> device, [2] time windows,
+ * [3] host threads that wrote the result planes (0: the device expanded them) */
+int rwrt_last_host_stats(rwrt_handle h, double *stats4);
 
 /* Roofline denominator: measured FP64 FMA throughput of the device (TFLOP/s, register-resident DFMA
  * chains).  Diagnostic only; used by bench.py next to MEASURED_PEAKS.json, which has no FP64 figure. */

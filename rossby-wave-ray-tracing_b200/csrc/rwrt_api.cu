@@ -1,4 +1,7 @@
 // rwrt_api.cu -- the C ABI of librwrt.so (include/rwrt.h): handle, buffers, launch sequencing.
+#include <atomic>
+#include <thread>
+#include <vector>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -10,6 +13,7 @@
 #include "../../include/rwrt.h"
 #include "rwrt_internal.h"
 #include "rwrt_rk45_params.h"
+#include "rwrt_hx.h"
 
 using namespace rwrt;
 
@@ -75,6 +79,22 @@ struct rwrt_ctx {
     cudaStream_t aux = nullptr;  // side stream for work that is independent of the integrator
     bool timed = false;
     double last_launches = 0, last_nlive = 0;
+    // host-side expansion (rwrt_real2d_host): pinned staging buffers, kept between calls
+    void *hx_stage[4] = {nullptr, nullptr, nullptr, nullptr}, *hx_rows[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t hx_stage_cap = 0, hx_rows_cap = 0;
+    int hx_nstage = 0;
+    const double *hx_row0 = nullptr;    // device (7, N): the t = 0 state of the current host-expanded run
+    double host_stats[4] = {0, 0, 0, 0};  // last rwrt_real2d_host: bytes D2H, bytes H2D, time windows, host threads
+    void release_hx_staging()
+    {
+        for (int i = 0; i < 4; ++i) {
+            if (hx_stage[i]) cudaFreeHost(hx_stage[i]);
+            if (hx_rows[i]) cudaFreeHost(hx_rows[i]);
+            hx_stage[i] = hx_rows[i] = nullptr;
+        }
+        hx_stage_cap = hx_rows_cap = 0;
+        hx_nstage = 0;
+    }
 
     Grid grid() const
     {
@@ -184,10 +204,9 @@ __global__ void __launch_bounds__(256) scatter_live_kernel(long long N, size_t p
 
 }  // namespace
 
-void launch_compact_live(long long N, int nt, const double *out7, int nsource, int nzwn, int32_t *live, int32_t *inv,
+void launch_compact_live(long long N, size_t pl, const double *out7, int nsource, int nzwn, int32_t *live, int32_t *inv,
                          unsigned long long *nlive_dev, int *block_counts, int nblocks, cudaStream_t s)
 {
-    size_t pl = (size_t)nt * N;
     count_live_kernel<<<nblocks, 256, 0, s>>>(N, pl, out7, nsource, nzwn, block_counts);
     scan_blocks_kernel<<<1, 1024, 0, s>>>(nblocks, block_counts, nlive_dev);
     scatter_live_kernel<<<nblocks, 256, 0, s>>>(N, pl, out7, nsource, nzwn, block_counts, live, inv);
@@ -286,6 +305,7 @@ int rwrt_destroy(rwrt_handle h)
     h->state.release();
     h->counters.release();
     h->blockcnt.release();
+    h->release_hx_staging();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -411,10 +431,19 @@ int rwrt_ray_init(rwrt_handle h, int nsource, const double *src_lon, const doubl
 // follow-up work (the host entry copies the finished rows to the host on another stream).
 typedef int (*window_hook)(void *ctx, int it_begin, int it_end, cudaStream_t s);
 
+// Host-side expansion (rwrt_real2d_host): the ray records of every time window travel to the host instead of the
+// reference-layout rows (13 GB instead of 23 GB on C2) and host threads write the caller's arrays from them.
+struct HostExpand;
+static int hx_on_window(HostExpand *hx, int w, int it_begin, int it_end, const double *rec_dev, int rec_rows,
+                        const int32_t *rows_done_dev, long long nlive, cudaStream_t s);
+static int hx_before_window(HostExpand *hx, int w, cudaStream_t s);
+static int hx_begin(HostExpand *hx, rwrt_handle h, long long nlive, int rec_rows, int nwin, cudaStream_t s);
+#define RWRT_HX_UNSUPPORTED 12345   /* internal: the caller falls back to device-side expansion */
+
 static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
                     double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
                     double *out7, int64_t *accepted, int64_t *attempts, int8_t *status, int64_t *total_accepted,
-                    void *stream, int nwin, window_hook hook, void *hook_ctx)
+                    void *stream, int nwin, window_hook hook, void *hook_ctx, HostExpand *hx = nullptr)
 {
     if (!h || nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45: bad sizes");
     if (!(tstep > 0)) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45: tstep must be positive");
@@ -449,7 +478,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         const char *er = getenv("RWRT_RECORDS");
         use_records = !(er && atoi(er) == 0);
         if (use_records && h->inv.reserve((size_t)N * sizeof(int32_t))) return fail(RWRT_ERR_NOMEM, "slot map allocation failed");
-        launch_compact_live(N, nt, out7, slot_order ? (int)1 : nsource, slot_order ? (int)1 : nzwn, (int32_t *)h->live.p,
+        launch_compact_live(N, hx ? (size_t)N : (size_t)nt * N, out7, slot_order ? (int)1 : nsource, slot_order ? (int)1 : nzwn, (int32_t *)h->live.p,
                             use_records ? (int32_t *)h->inv.p : nullptr, ctr + 2, (int *)h->blockcnt.p, nblocks, s);
     }
     unsigned long long nlive = 0;
@@ -474,6 +503,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     p.gmin = fmin(min_step_factor * tstep, (tstep - 0) * 0.001);
     p.cut = cut_off * tstep / 3600.;
     p.out = out7;
+    p.out_pl = hx ? (size_t)N : (size_t)nt * N;
     p.live = (const int32_t *)h->live.p;
     p.nlive = (long long)nlive;
     p.state = (double *)h->state.p;
@@ -492,6 +522,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     if ((long long)h->nmember * h->nlon_f * h->nlat >= (1LL << 30) - 1) coop = false;  // its fetch keys hold 30-bit point indices (103 GB of fields)
     p.coop = coop ? 1 : 0;
     if (!coop || nlive == 0) use_records = false;   // the record layout is a mode of the cooperative kernel
+    if (hx && !use_records) return RWRT_HX_UNSUPPORTED;
     p.rec = nullptr;
     p.rec_rows = 0;
     p.rows_done = nullptr;
@@ -511,7 +542,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     if (nwin > nt - 1) nwin = nt - 1;
     if (use_records) {
         // the records of one time window must fit beside everything else: more windows when memory is short
-        const size_t per_row = (size_t)nlive * 8 * sizeof(double);
+        const size_t per_row = (size_t)nlive * 8 * sizeof(double) * (hx ? 2 : 1);   // host expansion double-buffers the windows
         size_t budget = h->records.cap;             // a buffer from an earlier call is reused as it is ...
         if (budget < per_row * (size_t)((nt - 1 + nwin - 1) / nwin + 1)) {   // ... unless it is too small (cudaMemGetInfo costs ms)
             size_t free_b = 0, total_b = 0;
@@ -524,13 +555,17 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         int need_win = (nt - 1 + (max_rows - 1) - 1) / (max_rows - 1);
         if (need_win > nwin) nwin = need_win;
         if (nwin > nt - 1) nwin = nt - 1;
-        int rows = (nt - 1 + nwin - 1) / nwin + 1;  // rows of the largest window
-        if (h->records.reserve((size_t)nlive * rows * 8 * sizeof(double)) || h->rows_done.reserve((size_t)nlive * sizeof(int32_t)))
+        int rows = (nt - 1 + nwin - 1) / nwin + (hx ? 0 : 1);  // rows of the largest window (the host path copies whole buffers: no slack row)
+        if (h->records.reserve((size_t)nlive * rows * 8 * sizeof(double) * (hx ? 2 : 1)) || h->rows_done.reserve((size_t)nlive * sizeof(int32_t)))
             return fail(RWRT_ERR_NOMEM, "record buffer allocation failed (%llu rays x %d rows x 64 B)", nlive, rows);
         p.rec = (double *)h->records.p;
         p.rec_rows = rows;
         p.rows_done = (int32_t *)h->rows_done.p;
         p.inv = (const int32_t *)h->inv.p;
+        if (hx) {
+            int rc = hx_begin(hx, h, (long long)nlive, rows, nwin, s);
+            if (rc) return rc;
+        }
     }
     CU(cudaEventRecord(h->ev0, s));
     CU(cudaEventRecord(h->ev_fork, s));            // fork: the side stream starts after everything queued so far
@@ -547,11 +582,19 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         p.it_begin = 1 + (int)((long long)(nt - 1) * w / nwin);
         p.it_end = 1 + (int)((long long)(nt - 1) * (w + 1) / nwin);
         if (w > 0) CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));  // rewind the work queue
+        if (hx) {
+            p.rec = (double *)h->records.p + (size_t)(w & 1) * (size_t)nlive * p.rec_rows * 8;
+            int rc = hx_before_window(hx, w, s);    // device buffer (w & 1) and a host staging buffer must be free
+            if (rc) return rc;
+        }
         if (strict) launch_rk45_window_strict(p, integrate_blocks, s);
         else launch_rk45_window_fast(p, integrate_blocks, s);
         CU(cudaGetLastError());
         ++launches;
-        if (use_records) {                          // rows [it_begin, it_end) of the reference layout from the records
+        if (hx) {
+            int rc = hx_on_window(hx, w, p.it_begin, p.it_end, p.rec, p.rec_rows, p.rows_done, (long long)nlive, s);
+            if (rc) return rc;
+        } else if (use_records) {                   // rows [it_begin, it_end) of the reference layout from the records
             if (strict) launch_expand_records_strict(p, s);
             else launch_expand_records_fast(p, s);
             CU(cudaGetLastError());
@@ -568,6 +611,194 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     h->last_nlive = (double)nlive;
     if (total_accepted)
         CU(cudaMemcpyAsync(total_accepted, ctr + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    return RWRT_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Host-side expansion of the ray records (rwrt_real2d_host).
+//
+// The link to the host is the bottleneck of the host-buffer call (23.2 GB of reference-layout rows per C2 pass at
+// 34-55 GB/s).  Half of those bytes are redundant: NaN-root slots are constant / NaN in every row, dead rays are NaN.
+// So the records (64 B per live ray and row: 13 GB) cross the link, window by window, into pinned staging buffers,
+// and host threads write the caller's seven arrays from them: 8 consecutive slots x 1 row = one 64-byte line per
+// plane, non-temporal stores.  Device buffers alternate between two windows, staging buffers between HX_STAGES.
+// ---------------------------------------------------------------------------------------------
+constexpr int HX_STAGES = 4;
+struct HostExpand {
+    // set by the caller
+    double *out7_host = nullptr;            // (7, nt, N)
+    long long N = 0;
+    int nt = 0;
+    cudaStream_t copy_stream = nullptr;
+    // filled by hx_begin
+    long long nlive = 0;
+    int rec_rows = 0, nwin = 0;
+    std::vector<int32_t> inv;               // slot -> live index (host copy)
+    double *stage[HX_STAGES] = {};          // pinned (owned by the handle): nlive * rec_rows * 8 doubles each
+    int32_t *rows_stage[HX_STAGES] = {};    // pinned (owned by the handle): nlive ints each
+    std::vector<cudaEvent_t> kernel_done, copied;   // per window
+    std::vector<int> w_begin, w_end;
+    std::atomic<int> enqueued{0};           // windows whose D2H has been queued
+    std::vector<std::atomic<int>> *chunks_done = nullptr;   // per window: finished chunks
+    int nchunk = 0;
+    long long chunk_slots = 0;
+    std::vector<std::thread> workers;
+    std::atomic<int> next_task{0};
+    std::atomic<bool> abort{false};
+};
+
+static void hx_worker(HostExpand *hx, int device)
+{
+    cudaSetDevice(device);
+    const int total = hx->nwin * hx->nchunk;
+    for (;;) {
+        const int task = hx->next_task.fetch_add(1);
+        if (task >= total || hx->abort.load()) return;
+        const int w = task / hx->nchunk, c = task % hx->nchunk;
+        while (hx->enqueued.load(std::memory_order_acquire) <= w) {     // D2H of window w not queued yet
+            if (hx->abort.load()) return;
+            std::this_thread::yield();
+        }
+        if (cudaEventSynchronize(hx->copied[w]) != cudaSuccess) {
+            hx->abort.store(true);
+            return;
+        }
+        const long long s0 = (long long)c * hx->chunk_slots;
+        const long long s1 = s0 + hx->chunk_slots < hx->N ? s0 + hx->chunk_slots : hx->N;
+        HxView v;
+        v.out = hx->out7_host;
+        v.pl = (size_t)hx->nt * hx->N;
+        v.N = hx->N;
+        v.inv = hx->inv.data();
+        v.stage = hx->stage[w % HX_STAGES];
+        v.rows_done = hx->rows_stage[w % HX_STAGES];
+        v.rec_rows = hx->rec_rows;
+        hx_expand_rows(v, hx->w_begin[w], hx->w_end[w], s0, s1);
+        (*hx->chunks_done)[w].fetch_add(1, std::memory_order_release);
+    }
+}
+
+static int hx_begin(HostExpand *hx, rwrt_handle h, long long nlive, int rec_rows, int nwin, cudaStream_t s)
+{
+    hx->nlive = nlive;
+    hx->rec_rows = rec_rows;
+    hx->nwin = nwin;
+    hx->inv.resize((size_t)hx->N);
+    CU(cudaMemcpyAsync(hx->inv.data(), h->inv.p, (size_t)hx->N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    // row 0 (the t = 0 state, wr.py:768-781) goes to the caller's planes now: the workers read the constant values of
+    // NaN-root slots from it
+    CU(cudaMemcpy2DAsync(hx->out7_host, (size_t)hx->nt * hx->N * sizeof(double), h->hx_row0, (size_t)hx->N * sizeof(double),
+                         (size_t)hx->N * sizeof(double), 7, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    // pinned staging buffers live on the handle: pinning 2 GB costs more than a whole C2 pass
+    const size_t stage_bytes = (size_t)nlive * rec_rows * 8 * sizeof(double), rows_bytes = (size_t)nlive * sizeof(int32_t);
+    const int nstage = nwin < HX_STAGES ? nwin : HX_STAGES;
+    if (h->hx_stage_cap < stage_bytes || h->hx_rows_cap < rows_bytes || h->hx_nstage < nstage) {
+        h->release_hx_staging();
+        for (int i = 0; i < nstage; ++i) {
+            if (cudaMallocHost((void **)&h->hx_stage[i], stage_bytes) != cudaSuccess ||
+                cudaMallocHost((void **)&h->hx_rows[i], rows_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                h->release_hx_staging();
+                return fail(RWRT_ERR_NOMEM, "pinned staging allocation failed (%d x %zu bytes)", nstage, stage_bytes);
+            }
+        }
+        h->hx_stage_cap = stage_bytes;
+        h->hx_rows_cap = rows_bytes;
+        h->hx_nstage = nstage;
+    }
+    for (int i = 0; i < HX_STAGES; ++i) {
+        hx->stage[i] = (double *)h->hx_stage[i];
+        hx->rows_stage[i] = (int32_t *)h->hx_rows[i];
+    }
+    hx->kernel_done.assign(nwin, nullptr);
+    hx->copied.assign(nwin, nullptr);
+    hx->w_begin.assign(nwin, 0);
+    hx->w_end.assign(nwin, 0);
+    for (int w = 0; w < nwin; ++w) {
+        CU(cudaEventCreateWithFlags(&hx->kernel_done[w], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&hx->copied[w], cudaEventDisableTiming | cudaEventBlockingSync));
+    }
+    hx->chunks_done = new std::vector<std::atomic<int>>(nwin);
+    for (auto &a : *hx->chunks_done) a.store(0);
+    hx->chunk_slots = 4096;                     // multiple of 8: 64-byte lines stay whole when N is a multiple of 8
+    hx->nchunk = (int)((hx->N + hx->chunk_slots - 1) / hx->chunk_slots);
+    int nthreads = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("RWRT_HOST_THREADS")) nthreads = atoi(e);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    for (int i = 0; i < nthreads; ++i) hx->workers.emplace_back(hx_worker, hx, h->device);
+    h->host_stats[0] += (double)hx->N * (sizeof(int32_t) + 7 * sizeof(double)) + (double)nwin * (double)(stage_bytes + rows_bytes);
+    h->host_stats[2] = nwin;
+    h->host_stats[3] = nthreads;
+    return RWRT_OK;
+}
+
+// before window w's kernel: its device record buffer (w & 1) was last read by the copy of window w - 2
+static int hx_before_window(HostExpand *hx, int w, cudaStream_t s)
+{
+    if (w >= 2) CU(cudaStreamWaitEvent(s, hx->copied[w - 2], 0));
+    return RWRT_OK;
+}
+
+static int hx_on_window(HostExpand *hx, int w, int it_begin, int it_end, const double *rec_dev, int rec_rows,
+                        const int32_t *rows_done_dev, long long nlive, cudaStream_t s)
+{
+    hx->w_begin[w] = it_begin;
+    hx->w_end[w] = it_end;
+    if (w >= HX_STAGES) {                       // the staging buffer is reused: wait for its previous window on the host
+        while ((*hx->chunks_done)[w - HX_STAGES].load(std::memory_order_acquire) < hx->nchunk) {
+            if (hx->abort.load()) return fail(RWRT_ERR_CUDA, "host expansion aborted");
+            std::this_thread::yield();
+        }
+    }
+    CU(cudaEventRecord(hx->kernel_done[w], s));
+    CU(cudaStreamWaitEvent(hx->copy_stream, hx->kernel_done[w], 0));
+    // rows_done only grows, and a later window's kernel may already be raising it while this copy reads it: every
+    // value it can see marks the rows of window w of a ray that was alive at the end of window w as valid
+    CU(cudaMemcpyAsync(hx->rows_stage[w % HX_STAGES], rows_done_dev, (size_t)nlive * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       hx->copy_stream));
+    CU(cudaMemcpyAsync(hx->stage[w % HX_STAGES], rec_dev, (size_t)nlive * rec_rows * 8 * sizeof(double), cudaMemcpyDeviceToHost,
+                       hx->copy_stream));
+    CU(cudaEventRecord(hx->copied[w], hx->copy_stream));
+    hx->enqueued.store(w + 1, std::memory_order_release);
+    return RWRT_OK;
+}
+
+// joins the workers (after every window has been expanded when ok, at once otherwise) and frees the per-call objects
+static int hx_finish(HostExpand *hx, bool ok)
+{
+    if (!ok) hx->abort.store(true);
+    for (auto &t : hx->workers) t.join();
+    hx->workers.clear();
+    for (auto e : hx->kernel_done) if (e) cudaEventDestroy(e);
+    for (auto e : hx->copied) if (e) cudaEventDestroy(e);
+    hx->kernel_done.clear();
+    hx->copied.clear();
+    delete hx->chunks_done;
+    hx->chunks_done = nullptr;
+    return hx->abort.load() ? RWRT_ERR_CUDA : RWRT_OK;
+}
+
+// Host half of rwrt_real2d_host on its own (tests, and callers that move the records themselves): rows [row_begin,
+// row_end) of slots [slot_begin, slot_end) of the seven planes from the records of one time window.  Pure host code.
+int rwrt_host_expand_rows(double *out7_host, int nt, int64_t nslot, const int32_t *slot_to_ray, const double *records,
+                          const int32_t *rows_done, int rec_rows, int row_begin, int row_end, int64_t slot_begin,
+                          int64_t slot_end)
+{
+    if (!out7_host || !slot_to_ray || !records || !rows_done || nt < 1 || nslot < 0 || rec_rows < 1 || row_begin < 1 ||
+        row_end > nt || row_end - row_begin > rec_rows || slot_begin < 0 || slot_end > nslot)
+        return fail(RWRT_ERR_ARG, "rwrt_host_expand_rows: bad argument");
+    HxView v;
+    v.out = out7_host;
+    v.pl = (size_t)nt * (size_t)nslot;
+    v.N = nslot;
+    v.inv = slot_to_ray;
+    v.stage = records;
+    v.rows_done = rows_done;
+    v.rec_rows = rec_rows;
+    if (row_begin < row_end && slot_begin < slot_end) hx_expand_rows(v, row_begin, row_end, slot_begin, slot_end);
     return RWRT_OK;
 }
 
@@ -593,6 +824,7 @@ int rwrt_trim(rwrt_handle h)
     h->state.release();
     h->live.release();
     h->blockcnt.release();
+    h->release_hx_staging();
     return RWRT_OK;
 }
 
@@ -609,6 +841,13 @@ int rwrt_last_run_stats(rwrt_handle h, double *stats3)
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         stats3[2] = ms;
     }
+    return RWRT_OK;
+}
+
+int rwrt_last_host_stats(rwrt_handle h, double *stats4)
+{
+    if (!h || !stats4) return fail(RWRT_ERR_ARG, "rwrt_last_host_stats: NULL argument");
+    for (int i = 0; i < 4; ++i) stats4[i] = h->host_stats[i];
     return RWRT_OK;
 }
 
@@ -738,38 +977,41 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
     return rc;
 }
 
-int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
-                     const double *coslat, const double *sinlat, int nsource, const double *src_lon,
-                     const double *src_lat, const int32_t *src_member, int nzwn, const double *zwn, double freq, int nt,
-                     double tstep, double ttotal, double rtol, double atol, double min_step_factor, double cut_off,
-                     uint32_t flags, double *out7_host, int64_t *accepted_host, int8_t *status_host,
-                     int64_t *total_accepted_host, void *stream)
+static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
+                            const double *coslat, const double *sinlat, int nsource, const double *src_lon,
+                            const double *src_lat, const int32_t *src_member, int nzwn, const double *zwn, double freq, int nt,
+                            double tstep, double ttotal, double rtol, double atol, double min_step_factor, double cut_off,
+                            uint32_t flags, double *out7_host, int64_t *accepted_host, int8_t *status_host,
+                            int64_t *total_accepted_host, void *stream, bool use_hx)
 {
-    if (!h || !u || !v || !lon || !lat || !src_lon || !src_lat || !zwn || !out7_host)
-        return fail(RWRT_ERR_ARG, "rwrt_real2d_host: NULL argument");
-    if (nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_real2d_host: bad sizes");
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaSetDevice(h->device));
     const size_t ng = (size_t)h->nmember * h->nlon * h->nlat;
     const long long N = 3LL * nsource * nzwn;
     const size_t nout = (size_t)7 * nt * N;
-    // The integration runs in time windows; the rows of a finished window travel to the host on a second
-    // stream (contiguous copies in the reference layout) while the next window integrates.
+    // The integration runs in time windows; what a finished window produced travels to the host on a second stream
+    // while the next window integrates.
     int nwin = (int)((nout * sizeof(double)) >> 30);  // ~1 GB of trajectories per window (measured on C2: 1 / 4 / 10 / 24
                                                       // windows -> 683 / 631 / 548 / 492 ms per pass on the same box)
     if (const char *e = getenv("RWRT_HOST_WINDOWS")) nwin = atoi(e);
     if (nwin < 1) nwin = 1;
     if (nwin > 64) nwin = 64;
-    // one device arena for every input and output of the call
+    // one device arena for every input and output of the call; with host-side expansion the device holds only the
+    // t = 0 row of the seven planes (7 x N) -- the other rows exist as ray records in the library's window buffers
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     size_t o_u = carve(ng * 4), o_v = carve(ng * 4), o_lon = carve((size_t)h->nlon * 8), o_lat = carve((size_t)h->nlat * 8);
     size_t o_cl = carve((size_t)h->nlat * 8), o_sl = carve((size_t)h->nlat * 8);
     size_t o_slon = carve((size_t)nsource * 8), o_slat = carve((size_t)nsource * 8), o_mem = carve((size_t)nsource * 4);
     size_t o_zwn = carve((size_t)nzwn * 8), o_acc = carve((size_t)N * 8), o_st = carve((size_t)N), o_tot = carve(8);
-    size_t o_out = carve(nout * 8);
+    size_t o_out = carve(use_hx ? (size_t)7 * N * 8 : nout * 8);
     char *arena = nullptr;
     CU(cudaMalloc((void **)&arena, off));
+    h->host_stats[0] = (use_hx ? 0.0 : (double)nout * 8) + (accepted_host ? (double)N * 8 : 0.0) + (status_host ? (double)N : 0.0) + 8;
+    h->host_stats[1] = (double)ng * 8 + (double)h->nlon * 8 + (double)h->nlat * ((coslat && sinlat) ? 24 : 8) +
+                       (double)nsource * (src_member ? 20 : 16) + (double)nzwn * 8;
+    h->host_stats[2] = nwin;
+    h->host_stats[3] = 0;
     HostCopyCtx ctx;
     ctx.copy_stream = nullptr;
     ctx.ev[0] = ctx.ev[1] = nullptr;
@@ -779,6 +1021,10 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
     ctx.N = N;
     ctx.nt = nt;
     ctx.first = true;
+    HostExpand hx;
+    hx.out7_host = out7_host;
+    hx.N = N;
+    hx.nt = nt;
     int rc = RWRT_OK;
 #define CUX(call)                                                                                       \
     do {                                                                                                \
@@ -789,6 +1035,7 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
         }                                                                                               \
     } while (0)
     CUX(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
+    hx.copy_stream = ctx.copy_stream;
     CUX(cudaEventCreateWithFlags(&ctx.ev[0], cudaEventDisableTiming));
     CUX(cudaEventCreateWithFlags(&ctx.ev[1], cudaEventDisableTiming));
     CUX(cudaMemcpyAsync(arena + o_u, u, ng * 4, cudaMemcpyHostToDevice, s));
@@ -806,6 +1053,10 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
     }
     if (nzwn > 0) CUX(cudaMemcpyAsync(arena + o_zwn, zwn, (size_t)nzwn * 8, cudaMemcpyHostToDevice, s));
     CUX(cudaMemsetAsync(arena + o_tot, 0, 8, s));
+    if (use_hx) {   // counters and status of NaN-root slots are zero (expand_records writes them on the device path)
+        CUX(cudaMemsetAsync(arena + o_acc, 0, (size_t)N * 8, s));
+        CUX(cudaMemsetAsync(arena + o_st, 0, (size_t)N, s));
+    }
     {
         const int32_t *dmem = src_member ? (const int32_t *)(arena + o_mem) : nullptr;
         rc = rwrt_bs_ready(h, (const float *)(arena + o_u), (const float *)(arena + o_v), (const double *)(arena + o_lon),
@@ -813,14 +1064,15 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
                            (coslat && sinlat) ? (const double *)(arena + o_sl) : nullptr, nullptr, nullptr, s);
         if (rc) goto done;
         rc = rwrt_ray_init(h, nsource, (const double *)(arena + o_slon), (const double *)(arena + o_slat), dmem, nzwn,
-                           (const double *)(arena + o_zwn), freq, nt, (double *)(arena + o_out), s);
+                           (const double *)(arena + o_zwn), freq, use_hx ? 1 : nt, (double *)(arena + o_out), s);
         if (rc) goto done;
+        h->hx_row0 = (const double *)(arena + o_out);
         rc = run_rk45(h, nsource, dmem, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags,
                       (double *)(arena + o_out), (int64_t *)(arena + o_acc), nullptr, (int8_t *)(arena + o_st),
-                      (int64_t *)(arena + o_tot), s, nwin, host_copy_hook, &ctx);
-        if (rc) goto done;
+                      (int64_t *)(arena + o_tot), s, nwin, use_hx ? nullptr : host_copy_hook, &ctx, use_hx ? &hx : nullptr);
+        if (rc) goto done;      // RWRT_HX_UNSUPPORTED included: the caller runs the device-side expansion instead
     }
-    if (ctx.first && nout > 0)  // nothing was integrated (no live ray / nt == 1): plain copy of what there is
+    if (!use_hx && ctx.first && nout > 0)  // nothing was integrated (no live ray / nt == 1): plain copy of what there is
         CUX(cudaMemcpyAsync(out7_host, arena + o_out, nout * 8, cudaMemcpyDeviceToHost, s));
     if (accepted_host && N > 0) CUX(cudaMemcpyAsync(accepted_host, arena + o_acc, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
     if (status_host && N > 0) CUX(cudaMemcpyAsync(status_host, arena + o_st, (size_t)N, cudaMemcpyDeviceToHost, s));
@@ -828,6 +1080,11 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
     CUX(cudaStreamSynchronize(s));
     CUX(cudaStreamSynchronize(ctx.copy_stream));
 done:
+    if (use_hx) {
+        int rc2 = hx_finish(&hx, rc == RWRT_OK);    // joins the workers: every window is in the caller's arrays
+        if (rc == RWRT_OK && rc2) rc = fail(rc2, "host-side expansion failed");
+    }
+    h->hx_row0 = nullptr;
     if (ctx.copy_stream) {
         cudaStreamSynchronize(ctx.copy_stream);
         cudaStreamDestroy(ctx.copy_stream);
@@ -837,6 +1094,32 @@ done:
     cudaFree(arena);
     return rc;
 #undef CUX
+}
+
+int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double *lon, const double *lat,
+                     const double *coslat, const double *sinlat, int nsource, const double *src_lon,
+                     const double *src_lat, const int32_t *src_member, int nzwn, const double *zwn, double freq, int nt,
+                     double tstep, double ttotal, double rtol, double atol, double min_step_factor, double cut_off,
+                     uint32_t flags, double *out7_host, int64_t *accepted_host, int8_t *status_host,
+                     int64_t *total_accepted_host, void *stream)
+{
+    if (!h || !u || !v || !lon || !lat || !src_lon || !src_lat || !zwn || !out7_host)
+        return fail(RWRT_ERR_ARG, "rwrt_real2d_host: NULL argument");
+    if (nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_real2d_host: bad sizes");
+    // Default: the ray records travel and host threads write the caller's arrays from them (RWRT_HOST_EXPAND=0: the
+    // device expands and the reference-layout rows travel).  Runs without live rays / on the per-lane kernel have no
+    // records: they take the second form.
+    bool use_hx = nt >= 2 && (long long)nsource * nzwn > 0;
+    if (const char *e = getenv("RWRT_HOST_EXPAND")) use_hx = use_hx && atoi(e) != 0;
+    if (use_hx) {
+        int rc = real2d_host_impl(h, u, v, lon, lat, coslat, sinlat, nsource, src_lon, src_lat, src_member, nzwn, zwn, freq, nt,
+                                  tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7_host, accepted_host,
+                                  status_host, total_accepted_host, stream, true);
+        if (rc != RWRT_HX_UNSUPPORTED) return rc;
+    }
+    return real2d_host_impl(h, u, v, lon, lat, coslat, sinlat, nsource, src_lon, src_lat, src_member, nzwn, zwn, freq, nt, tstep,
+                            ttotal, rtol, atol, min_step_factor, cut_off, flags, out7_host, accepted_host, status_host,
+                            total_accepted_host, stream, false);
 }
 
 }  // extern "C"

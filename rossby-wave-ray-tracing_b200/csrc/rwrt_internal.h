@@ -53,7 +53,7 @@ void launch_grid_accumulate(long long nslot, int nt, const double *out7, double 
 int measure_fp64_peak(int sm_count, double *tflops, cudaStream_t s);
 
 // rwrt_api.cu helpers
-void launch_compact_live(long long N, int nt, const double *out7, int nsource, int nzwn, int32_t *live, int32_t *inv,
+void launch_compact_live(long long N, size_t plane_stride, const double *out7, int nsource, int nzwn, int32_t *live, int32_t *inv,
                          unsigned long long *nlive_dev, int *block_counts, int nblocks, cudaStream_t s);
 
 }  // namespace rwrt

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) rk45_prepare(RunParams p)
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.nlive) return;
     long long slot = p.live[i];
-    const size_t pl = (size_t)p.nt * p.N;
+    const size_t pl = p.out_pl;
     double y[5], f[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) y[c] = p.out[c * pl + slot];

@@ -13,6 +13,7 @@ struct RunParams {
     long long N;                // slots = 3 * nsource * nzwn
     double tstep, ttotal, rtol, atol, gmin, cut;
     double *out;                // 7 planes, each (nt, N)
+    size_t out_pl;              // doubles between the planes of `out` (nt * N; N when only row 0 exists: host-side expansion)
     const int32_t *live;        // compacted list of live slots
     long long nlive;
     double *state;              // (nlive, RWRT_STATE): y[5], f[5], h_abs, cos(prev lat), t, prev lon, prev lat, counters

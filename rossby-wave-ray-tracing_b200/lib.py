@@ -20,7 +20,7 @@ RAY_NO_ROOT, RAY_ALIVE, RAY_POLE, RAY_SPEED, RAY_NAN = 0, 1, 2, 3, 4
 SYMBOLS = (
     "rwrt_abi_version", "rwrt_last_error", "rwrt_device_count", "rwrt_host_alloc", "rwrt_host_free",
     "rwrt_create", "rwrt_destroy", "rwrt_trim", "rwrt_bs_ready", "rwrt_bs_set_fields", "rwrt_sample_mercator", "rwrt_sample_mercator18", "rwrt_rhs",
-    "rwrt_ray_init", "rwrt_ray_run_rk45", "rwrt_ray_run_rk45_d2h", "rwrt_ray_run_rk4", "rwrt_grid_accumulate", "rwrt_real2d_host", "rwrt_last_run_stats", "rwrt_measure_fp64_peak",
+    "rwrt_ray_init", "rwrt_ray_run_rk45", "rwrt_ray_run_rk45_d2h", "rwrt_ray_run_rk4", "rwrt_grid_accumulate", "rwrt_real2d_host", "rwrt_host_expand_rows", "rwrt_last_host_stats", "rwrt_last_run_stats", "rwrt_measure_fp64_peak",
     "rwrt_shsf_plan_create", "rwrt_shsf_out_shape", "rwrt_shsf_apply", "rwrt_shsf_plan_destroy",
 )
 
@@ -63,7 +63,9 @@ def load():
     L.rwrt_grid_accumulate.argtypes = [vp, i64, i32, vp, f64, f64, i32, i32, vp, vp, vp, vp]
     L.rwrt_real2d_host.argtypes = ([vp] + [vp] * 6 + [i32, vp, vp, vp, i32, vp, f64, i32] + [f64] * 6 +
                                    [u32, vp, vp, vp, vp, vp])
+    L.rwrt_host_expand_rows.argtypes = [vp, i32, i64, vp, vp, vp, i32, i32, i32, i64, i64]
     L.rwrt_last_run_stats.argtypes = [vp, C.POINTER(f64)]
+    L.rwrt_last_host_stats.argtypes = [vp, C.POINTER(f64)]
     L.rwrt_measure_fp64_peak.argtypes = [vp, C.POINTER(f64)]
     L.rwrt_shsf_plan_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
     L.rwrt_shsf_out_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]

@@ -169,3 +169,48 @@ def test_schedule_and_gather_independence(monkeypatch):
                 del out
     finally:
         L.rwrt_destroy(h)
+
+
+def test_host_entry_quarter_size(monkeypatch):
+    """rwrt_real2d_host at a quarter of C2 (287 k slots, 5.8 GB of result planes in pageable host memory): the default
+    form (ray records cross the link window by window into pinned staging buffers, host threads write the planes --
+    every staging buffer and both device window buffers are reused several times) and the device-expanded form
+    (RWRT_HOST_EXPAND=0) must both return the bits of the device-resident run, twice in a row on one handle."""
+    nlon, nlat = 360, 181
+    slon_deg, slat_deg = synthetic.all_gridpoint_sources(nlon, nlat, 88.0)
+    slon_deg, slat_deg = slon_deg[1::4], slat_deg[1::4]
+    zwn = np.arange(1.0, 7.0)
+    ns, nz = len(slon_deg), len(zwn)
+    L, h, d, dev = _setup(nlon, nlat, slon_deg, slat_deg, zwn)
+    try:
+        out, acc, status, total, nt, N = _run(L, h, d, dev, ns, nz)
+        ck = _checksum(out)
+        acc0, status0 = acc.cpu().numpy(), status.cpu().numpy()
+        del out
+        __import__("torch").cuda.empty_cache()
+        u, v = synthetic.clim(nlon, nlat)
+        lon, lat = synthetic.grid_coords(nlon, nlat)
+        cl, sn = np.cos(lat), np.sin(lat)
+        slon, slat = np.radians(slon_deg), np.radians(slat_deg)
+        host = np.empty((7, nt, N))
+        for env in ({}, {"RWRT_HOST_THREADS": "3", "RWRT_HOST_WINDOWS": "11"}, {"RWRT_HOST_EXPAND": "0"}, {}):
+            for k, val in env.items():
+                monkeypatch.setenv(k, val)
+            try:
+                host.fill(-7.0)
+                acc_h = np.full(N, -1, dtype=np.int64)
+                st_h = np.full(N, -1, dtype=np.int8)
+                tot_h = np.zeros(1, dtype=np.int64)
+                lib.check(L.rwrt_real2d_host(h, lib.ptr(u), lib.ptr(v), lib.ptr(lon), lib.ptr(lat), lib.ptr(cl), lib.ptr(sn), ns,
+                                             lib.ptr(slon), lib.ptr(slat), None, nz, lib.ptr(zwn), 0.0, nt, TSTEP,
+                                             DAYS * 86400.0, 1e-6, 1e-6, 1e-3, 0.1, lib.MODE_FAST, lib.ptr(host), lib.ptr(acc_h),
+                                             lib.ptr(st_h), lib.ptr(tot_h), None), "rwrt_real2d_host")
+            finally:
+                for k in env:
+                    monkeypatch.delenv(k)
+            with np.errstate(over="ignore"):
+                ck_h = int(host.reshape(-1).view(np.int64).sum(dtype=np.int64))
+            assert ck_h == ck, env
+            assert int(tot_h[0]) == total and np.array_equal(acc_h, acc0) and np.array_equal(st_h, status0), env
+    finally:
+        L.rwrt_destroy(h)

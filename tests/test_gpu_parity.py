@@ -210,8 +210,9 @@ def test_batch_composition_independence():
 
 
 def test_c_abi_host_entry_equals_facade(monkeypatch):
-    """rwrt_real2d_host (host pointers, H2D/D2H inside; integration in time windows whose finished rows are
-    copied back while the next window runs) returns what the facade returns -- with 1 and with 4 windows."""
+    """rwrt_real2d_host (host pointers, H2D/D2H inside; integration in time windows whose ray records -- or, with
+    RWRT_HOST_EXPAND=0, finished rows -- are copied back while the next window runs) returns what the facade returns,
+    with 1 ... 30 windows (more windows than staging buffers: every buffer is reused)."""
     u, v = synthetic.clim(144, 73)
     ns = 120
     sl, sa = synthetic.random_sources(ns, 3)
@@ -224,8 +225,9 @@ def test_c_abi_host_entry_equals_facade(monkeypatch):
     L = lib.load()
     nt = w.nt
     cl, sn = np.cos(lat), np.sin(lat)
-    for chunk_mb in ("1", "4"):
+    for chunk_mb, expand in (("1", "1"), ("4", "1"), ("9", "1"), ("30", "1"), ("1", "0"), ("4", "0")):
         monkeypatch.setenv("RWRT_HOST_WINDOWS", chunk_mb)
+        monkeypatch.setenv("RWRT_HOST_EXPAND", expand)   # 1: records travel, host threads expand; 0: device expands
         h = lib.vp()
         lib.check(L.rwrt_create(0, 144, 73, 1, 1, C.byref(h)))
         out = np.full((7, nt, 3, ns, 3), -7.0)
@@ -237,7 +239,7 @@ def test_c_abi_host_entry_equals_facade(monkeypatch):
                                      days * 86400.0, 1e-6, 1e-6, 1e-3, 0.1, lib.MODE_FAST, lib.ptr(out), lib.ptr(acc),
                                      lib.ptr(status), lib.ptr(total), None), "rwrt_real2d_host")
         for k, n in enumerate(parity.NAMES):
-            assert np.array_equal(out[k], getattr(w, n), equal_nan=True), (chunk_mb, n)
+            assert np.array_equal(out[k], getattr(w, n), equal_nan=True), (chunk_mb, expand, n)
         assert np.array_equal(acc.reshape(3, ns, 3), w.accepted) and int(total[0]) == w.total_accepted
         assert np.array_equal(status.reshape(3, ns, 3), w.status)
         L.rwrt_destroy(h)
