@@ -157,10 +157,11 @@ int rwrt_grid_accumulate(rwrt_handle h, int64_t nslot, int nt, const double *out
  * Whole ray path with HOST buffers (the call main_wr.real2d_hnf makes, main_wr.py:66-89, minus
  * NetCDF): H2D of u, v, coordinates, sources; BS.ready; ray_initial; RK45; the seven result arrays
  * (wr.py:767-781) in out7_host.  Synchronises before returning.
- * The integration runs in time windows.  Default: the 64-byte ray records of a finished window travel to pinned
- * staging buffers kept on the handle while the next window integrates, and host threads (RWRT_HOST_THREADS,
- * default: all cores) write the caller's planes from them -- about half of the reference-layout bytes are NaN /
- * constant rows that never need to cross the link, and out7_host may be pageable.  RWRT_HOST_EXPAND=0: the device
+ * The integration runs in time windows.  Default: the rows of a finished window travel as seven packed planes of
+ * the LIVE rays (56 bytes per live ray and row) to pinned staging buffers kept on the handle while the next window
+ * integrates, and host threads (RWRT_HOST_THREADS, default: all cores) write the caller's planes from them -- about
+ * half of the reference-layout bytes are NaN / constant rows that never need to cross the link, and out7_host may
+ * be pageable.  RWRT_HOST_EXPAND=0: the device
  * expands the records and the reference-layout rows travel (fast only into pinned memory, rwrt_host_alloc).
  * Both forms give the same bits.
  */
@@ -173,15 +174,14 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
 
 /*
  * Host half of rwrt_real2d_host on its own (pure host code, no device needed): writes rows [row_begin, row_end) of
- * slots [slot_begin, slot_end) of the seven planes out7_host (7, nt, nslot) from the ray records of one time window.
- * records: [ray][rec_rows][8] doubles = (lon, lat, k, l, A, u_g, v_g, pad) for rows row_begin ...; slot_to_ray[slot]
- * = index of the slot's ray, < 0 for a slot without a real root (its planes 0..4 repeat row 0 of out7_host, u_g and
- * v_g are NaN: wr.py:768-781 and SURVEY appendix C-7); rows >= rows_done[ray] are NaN in all planes (wr.py:838-855).
- * row_begin >= 1 (row 0 is the t = 0 state and must already be in out7_host), row_end - row_begin <= rec_rows.
+ * slots [slot_begin, slot_end) of the seven planes out7_host (7, nt, nslot) from the packed rows of one time window.
+ * packed: (7, row_end - row_begin, nray) doubles = planes (lon, lat, k, l, A, u_g, v_g) of the nray >= 1 live rays
+ * (NaN in all planes once a ray is dead, wr.py:838-855); slot_to_ray[slot] = index of the slot's ray, < 0 for a slot
+ * without a real root (its planes 0..4 repeat row 0 of out7_host, u_g and v_g are NaN: wr.py:768-781 and SURVEY
+ * appendix C-7).  row_begin >= 1: row 0 is the t = 0 state and must already be in out7_host.
  */
-int rwrt_host_expand_rows(double *out7_host, int nt, int64_t nslot, const int32_t *slot_to_ray, const double *records,
-                          const int32_t *rows_done, int rec_rows, int row_begin, int row_end, int64_t slot_begin,
-                          int64_t slot_end);
+int rwrt_host_expand_rows(double *out7_host, int nt, int64_t nslot, const int32_t *slot_to_ray, const double *packed,
+                          int64_t nray, int row_begin, int row_end, int64_t slot_begin, int64_t slot_end);
 
 /* Releases the handle's scratch memory (ray records -- 64 B per live ray and output row of a time window --, ray
  * state, work lists, pinned staging buffers of rwrt_real2d_host).  The next run allocates again.  The fields stay. */

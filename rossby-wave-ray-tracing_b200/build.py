@@ -29,6 +29,7 @@ UNITS = {
     "rwrt_rk45_fast.cu": [],
     "rwrt_rk45_strict.cu": ["-fmad=false"],
     "rwrt_shsf.cu": [],
+    "rwrt_hx.cpp": [],       # host code only (the host half of rwrt_real2d_host), straight to the host compiler
 }
 
 
@@ -38,7 +39,7 @@ def _deps():
 
 
 def _compile(unit, flags, log, objdir=None):
-    obj = os.path.join(objdir or OBJ, unit.replace(".cu", ".o"))
+    obj = os.path.join(objdir or OBJ, os.path.splitext(unit)[0] + ".o")
     cmd = [NVCC, *ARCH, *[c for c in COMMON if not c.startswith("--use_fast_math")], *flags, "-c",
            os.path.join(CSRC, unit), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -53,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in _deps()):
         return LIB
     log = []
-    with ThreadPoolExecutor(max_workers=7) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(lambda kv: _compile(kv[0], kv[1], log), UNITS.items()))
     cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -72,7 +73,7 @@ def build_variant(out: str, extra: list) -> str:
     objdir = out + ".obj"
     os.makedirs(objdir, exist_ok=True)
     log = []
-    with ThreadPoolExecutor(max_workers=7) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(lambda kv: _compile(kv[0], kv[1] + extra, log, objdir), UNITS.items()))
     r = subprocess.run([NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:

@@ -1,5 +1,7 @@
 // rwrt_api.cu -- the C ABI of librwrt.so (include/rwrt.h): handle, buffers, launch sequencing.
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <cmath>
@@ -74,14 +76,14 @@ struct rwrt_ctx {
     int sm_count = 0;
     bool ready = false;
     double lon0 = 0, dlon = 0, lat0 = 0, dlat = 0;
-    DevBuf fpk, scratch, trig, live, state, counters, blockcnt, inv, rows_done, records;
+    DevBuf fpk, scratch, trig, live, state, counters, blockcnt, inv, rows_done, records, packed;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t aux = nullptr;  // side stream for work that is independent of the integrator
     bool timed = false;
     double last_launches = 0, last_nlive = 0;
     // host-side expansion (rwrt_real2d_host): pinned staging buffers, kept between calls
-    void *hx_stage[4] = {nullptr, nullptr, nullptr, nullptr}, *hx_rows[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t hx_stage_cap = 0, hx_rows_cap = 0;
+    void *hx_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t hx_stage_cap = 0;
     int hx_nstage = 0;
     const double *hx_row0 = nullptr;    // device (7, N): the t = 0 state of the current host-expanded run
     double host_stats[4] = {0, 0, 0, 0};  // last rwrt_real2d_host: bytes D2H, bytes H2D, time windows, host threads
@@ -89,10 +91,9 @@ struct rwrt_ctx {
     {
         for (int i = 0; i < 4; ++i) {
             if (hx_stage[i]) cudaFreeHost(hx_stage[i]);
-            if (hx_rows[i]) cudaFreeHost(hx_rows[i]);
-            hx_stage[i] = hx_rows[i] = nullptr;
+            hx_stage[i] = nullptr;
         }
-        hx_stage_cap = hx_rows_cap = 0;
+        hx_stage_cap = 0;
         hx_nstage = 0;
     }
 
@@ -211,6 +212,65 @@ void launch_compact_live(long long N, size_t pl, const double *out7, int nsource
     scan_blocks_kernel<<<1, 1024, 0, s>>>(nblocks, block_counts, nlive_dev);
     scatter_live_kernel<<<nblocks, 256, 0, s>>>(N, pl, out7, nsource, nzwn, block_counts, live, inv);
 }
+
+// ---------------------------------------------------------------------------------------------
+// pack_records: the ray records of one time window, [ray][rec_rows][8] as the integrator writes them, become seven
+// planes over the LIVE rays, packed[plane][row][ray] -- the form that crosses the link in rwrt_real2d_host (56 bytes
+// per live ray and row, no pad, rows of dead rays NaN like wr.py:838-855 leaves them).  Shared-memory transpose:
+// a ray's rows are read 1 KB at a time, planes are written 256 bytes at a time.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int PK_RAYS = 32, PK_ROWS = 16, PK_STRIDE = PK_ROWS * 8 + 1;   // odd stride: conflict-free column reads
+__global__ void __launch_bounds__(256) pack_records_kernel(const double *rec, int rec_rows, const int32_t *rows_done,
+                                                           long long nlive, int it_begin, int it_end, double *packed)
+{
+    __shared__ double tile[PK_RAYS * PK_STRIDE];
+    const long long ray0 = (long long)blockIdx.x * PK_RAYS;
+    const int row0 = it_begin + blockIdx.y * PK_ROWS;
+    const int len = it_end - it_begin;
+    const double n = __longlong_as_double(0x7ff8000000000000LL);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rr = lane >> 2, c = lane & 3;     // row within a pass of 8, 16-byte piece of the record
+#pragma unroll
+    for (int q = 0; q < PK_RAYS / 8; ++q) {
+        const int s = warp + 8 * q;
+        const long long li = ray0 + s;
+        if (li >= nlive) break;
+        const int rd = rows_done[li];
+        const double2 *r2 = reinterpret_cast<const double2 *>(rec + ((size_t)li * rec_rows) * 8);
+        double *t = tile + s * PK_STRIDE;
+#pragma unroll
+        for (int hh = 0; hh < PK_ROWS / 8; ++hh) {
+            const int it = row0 + rr + 8 * hh;
+            double2 v = make_double2(n, n);
+            if (it < rd && it < it_end) v = __ldcs(r2 + (size_t)(it - it_begin) * 4 + c);
+            t[(rr + 8 * hh) * 8 + 2 * c] = v.x;
+            t[(rr + 8 * hh) * 8 + 2 * c + 1] = v.y;
+        }
+    }
+    __syncthreads();
+    const long long li = ray0 + lane;
+#pragma unroll
+    for (int j = 0; j < PK_ROWS / 8; ++j) {
+        const int r = warp + 8 * j, it = row0 + r;
+        if (it >= it_end) break;
+        if (li < nlive) {
+#pragma unroll
+            for (int plane = 0; plane < 7; ++plane)
+                __stcs(packed + ((size_t)plane * len + (it - it_begin)) * (size_t)nlive + li, tile[lane * PK_STRIDE + r * 8 + plane]);
+        }
+    }
+}
+}  // namespace
+
+void launch_pack_records(const double *rec, int rec_rows, const int32_t *rows_done, long long nlive, int it_begin, int it_end,
+                         double *packed, cudaStream_t s)
+{
+    const int len = it_end - it_begin;
+    if (nlive <= 0 || len <= 0) return;
+    pack_records_kernel<<<dim3((unsigned)((nlive + PK_RAYS - 1) / PK_RAYS), (len + PK_ROWS - 1) / PK_ROWS), 256, 0, s>>>(
+        rec, rec_rows, rows_done, nlive, it_begin, it_end, packed);
+}
 }  // namespace rwrt
 
 // ---------------------------------------------------------------------------------------------
@@ -299,6 +359,7 @@ int rwrt_destroy(rwrt_handle h)
     h->inv.release();
     h->rows_done.release();
     h->records.release();
+    h->packed.release();
     h->scratch.release();
     h->trig.release();
     h->live.release();
@@ -434,9 +495,8 @@ typedef int (*window_hook)(void *ctx, int it_begin, int it_end, cudaStream_t s);
 // Host-side expansion (rwrt_real2d_host): the ray records of every time window travel to the host instead of the
 // reference-layout rows (13 GB instead of 23 GB on C2) and host threads write the caller's arrays from them.
 struct HostExpand;
-static int hx_on_window(HostExpand *hx, int w, int it_begin, int it_end, const double *rec_dev, int rec_rows,
+static int hx_on_window(HostExpand *hx, rwrt_handle h, int w, int it_begin, int it_end, const double *rec_dev, int rec_rows,
                         const int32_t *rows_done_dev, long long nlive, cudaStream_t s);
-static int hx_before_window(HostExpand *hx, int w, cudaStream_t s);
 static int hx_begin(HostExpand *hx, rwrt_handle h, long long nlive, int rec_rows, int nwin, cudaStream_t s);
 #define RWRT_HX_UNSUPPORTED 12345   /* internal: the caller falls back to device-side expansion */
 
@@ -542,7 +602,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     if (nwin > nt - 1) nwin = nt - 1;
     if (use_records) {
         // the records of one time window must fit beside everything else: more windows when memory is short
-        const size_t per_row = (size_t)nlive * 8 * sizeof(double) * (hx ? 2 : 1);   // host expansion double-buffers the windows
+        const size_t per_row = (size_t)nlive * (8 + (hx ? 14 : 0)) * sizeof(double);   // host path: + two packed window buffers (7 doubles per row each)
         size_t budget = h->records.cap;             // a buffer from an earlier call is reused as it is ...
         if (budget < per_row * (size_t)((nt - 1 + nwin - 1) / nwin + 1)) {   // ... unless it is too small (cudaMemGetInfo costs ms)
             size_t free_b = 0, total_b = 0;
@@ -556,7 +616,8 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         if (need_win > nwin) nwin = need_win;
         if (nwin > nt - 1) nwin = nt - 1;
         int rows = (nt - 1 + nwin - 1) / nwin + (hx ? 0 : 1);  // rows of the largest window (the host path copies whole buffers: no slack row)
-        if (h->records.reserve((size_t)nlive * rows * 8 * sizeof(double) * (hx ? 2 : 1)) || h->rows_done.reserve((size_t)nlive * sizeof(int32_t)))
+        if (h->records.reserve((size_t)nlive * rows * 8 * sizeof(double)) || h->rows_done.reserve((size_t)nlive * sizeof(int32_t)) ||
+            (hx && h->packed.reserve((size_t)nlive * rows * 14 * sizeof(double))))
             return fail(RWRT_ERR_NOMEM, "record buffer allocation failed (%llu rays x %d rows x 64 B)", nlive, rows);
         p.rec = (double *)h->records.p;
         p.rec_rows = rows;
@@ -582,17 +643,12 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         p.it_begin = 1 + (int)((long long)(nt - 1) * w / nwin);
         p.it_end = 1 + (int)((long long)(nt - 1) * (w + 1) / nwin);
         if (w > 0) CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));  // rewind the work queue
-        if (hx) {
-            p.rec = (double *)h->records.p + (size_t)(w & 1) * (size_t)nlive * p.rec_rows * 8;
-            int rc = hx_before_window(hx, w, s);    // device buffer (w & 1) and a host staging buffer must be free
-            if (rc) return rc;
-        }
         if (strict) launch_rk45_window_strict(p, integrate_blocks, s);
         else launch_rk45_window_fast(p, integrate_blocks, s);
         CU(cudaGetLastError());
         ++launches;
         if (hx) {
-            int rc = hx_on_window(hx, w, p.it_begin, p.it_end, p.rec, p.rec_rows, p.rows_done, (long long)nlive, s);
+            int rc = hx_on_window(hx, h, w, p.it_begin, p.it_end, p.rec, p.rec_rows, p.rows_done, (long long)nlive, s);
             if (rc) return rc;
         } else if (use_records) {                   // rows [it_begin, it_end) of the reference layout from the records
             if (strict) launch_expand_records_strict(p, s);
@@ -635,9 +691,8 @@ struct HostExpand {
     long long nlive = 0;
     int rec_rows = 0, nwin = 0;
     std::vector<int32_t> inv;               // slot -> live index (host copy)
-    double *stage[HX_STAGES] = {};          // pinned (owned by the handle): nlive * rec_rows * 8 doubles each
-    int32_t *rows_stage[HX_STAGES] = {};    // pinned (owned by the handle): nlive ints each
-    std::vector<cudaEvent_t> kernel_done, copied;   // per window
+    double *stage[HX_STAGES] = {};          // pinned (owned by the handle): packed rows of one window, 7 x rows x nlive doubles
+    std::vector<cudaEvent_t> packed_ev, copied;     // per window
     std::vector<int> w_begin, w_end;
     std::atomic<int> enqueued{0};           // windows whose D2H has been queued
     std::vector<std::atomic<int>> *chunks_done = nullptr;   // per window: finished chunks
@@ -646,6 +701,8 @@ struct HostExpand {
     std::vector<std::thread> workers;
     std::atomic<int> next_task{0};
     std::atomic<bool> abort{false};
+    std::mutex mu;                          // waits (window queued / window expanded) sleep on cv instead of spinning:
+    std::condition_variable cv;             // the launching thread and the CUDA driver threads need the cores too
 };
 
 static void hx_worker(HostExpand *hx, int device)
@@ -656,12 +713,17 @@ static void hx_worker(HostExpand *hx, int device)
         const int task = hx->next_task.fetch_add(1);
         if (task >= total || hx->abort.load()) return;
         const int w = task / hx->nchunk, c = task % hx->nchunk;
-        while (hx->enqueued.load(std::memory_order_acquire) <= w) {     // D2H of window w not queued yet
-            if (hx->abort.load()) return;
-            std::this_thread::yield();
+        if (hx->enqueued.load(std::memory_order_acquire) <= w) {        // D2H of window w not queued yet
+            std::unique_lock<std::mutex> lk(hx->mu);
+            hx->cv.wait(lk, [&] { return hx->enqueued.load(std::memory_order_acquire) > w || hx->abort.load(); });
         }
+        if (hx->abort.load()) return;
         if (cudaEventSynchronize(hx->copied[w]) != cudaSuccess) {
-            hx->abort.store(true);
+            {
+                std::lock_guard<std::mutex> lk(hx->mu);
+                hx->abort.store(true);
+            }
+            hx->cv.notify_all();
             return;
         }
         const long long s0 = (long long)c * hx->chunk_slots;
@@ -671,11 +733,14 @@ static void hx_worker(HostExpand *hx, int device)
         v.pl = (size_t)hx->nt * hx->N;
         v.N = hx->N;
         v.inv = hx->inv.data();
-        v.stage = hx->stage[w % HX_STAGES];
-        v.rows_done = hx->rows_stage[w % HX_STAGES];
-        v.rec_rows = hx->rec_rows;
-        hx_expand_rows(v, hx->w_begin[w], hx->w_end[w], s0, s1);
-        (*hx->chunks_done)[w].fetch_add(1, std::memory_order_release);
+        v.packed = hx->stage[w % HX_STAGES];
+        v.nray = hx->nlive;
+        v.rows = hx->w_end[w] - hx->w_begin[w];
+        hx_expand_rows(v, hx->w_begin[w], s0, s1);
+        if ((*hx->chunks_done)[w].fetch_add(1, std::memory_order_acq_rel) + 1 == hx->nchunk) {   // window w is in the caller's arrays
+            std::lock_guard<std::mutex> lk(hx->mu);
+            hx->cv.notify_all();
+        }
     }
 }
 
@@ -692,113 +757,111 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, long long nlive, int rec_rows
                          (size_t)hx->N * sizeof(double), 7, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     // pinned staging buffers live on the handle: pinning 2 GB costs more than a whole C2 pass
-    const size_t stage_bytes = (size_t)nlive * rec_rows * 8 * sizeof(double), rows_bytes = (size_t)nlive * sizeof(int32_t);
+    const size_t stage_bytes = (size_t)nlive * rec_rows * 7 * sizeof(double);
     const int nstage = nwin < HX_STAGES ? nwin : HX_STAGES;
-    if (h->hx_stage_cap < stage_bytes || h->hx_rows_cap < rows_bytes || h->hx_nstage < nstage) {
+    if (h->hx_stage_cap < stage_bytes || h->hx_nstage < nstage) {
         h->release_hx_staging();
         for (int i = 0; i < nstage; ++i) {
-            if (cudaMallocHost((void **)&h->hx_stage[i], stage_bytes) != cudaSuccess ||
-                cudaMallocHost((void **)&h->hx_rows[i], rows_bytes) != cudaSuccess) {
+            if (cudaMallocHost((void **)&h->hx_stage[i], stage_bytes) != cudaSuccess) {
                 cudaGetLastError();
                 h->release_hx_staging();
                 return fail(RWRT_ERR_NOMEM, "pinned staging allocation failed (%d x %zu bytes)", nstage, stage_bytes);
             }
         }
         h->hx_stage_cap = stage_bytes;
-        h->hx_rows_cap = rows_bytes;
         h->hx_nstage = nstage;
     }
-    for (int i = 0; i < HX_STAGES; ++i) {
-        hx->stage[i] = (double *)h->hx_stage[i];
-        hx->rows_stage[i] = (int32_t *)h->hx_rows[i];
-    }
-    hx->kernel_done.assign(nwin, nullptr);
+    for (int i = 0; i < HX_STAGES; ++i) hx->stage[i] = (double *)h->hx_stage[i];
+    hx->packed_ev.assign(nwin, nullptr);
     hx->copied.assign(nwin, nullptr);
     hx->w_begin.assign(nwin, 0);
     hx->w_end.assign(nwin, 0);
     for (int w = 0; w < nwin; ++w) {
-        CU(cudaEventCreateWithFlags(&hx->kernel_done[w], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&hx->packed_ev[w], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&hx->copied[w], cudaEventDisableTiming | cudaEventBlockingSync));
     }
     hx->chunks_done = new std::vector<std::atomic<int>>(nwin);
     for (auto &a : *hx->chunks_done) a.store(0);
-    hx->chunk_slots = 4096;                     // multiple of 8: 64-byte lines stay whole when N is a multiple of 8
+    hx->chunk_slots = HX_CHUNK;                 // multiple of 8: 64-byte lines stay whole when N is a multiple of 8
     hx->nchunk = (int)((hx->N + hx->chunk_slots - 1) / hx->chunk_slots);
     int nthreads = (int)std::thread::hardware_concurrency();
     if (const char *e = getenv("RWRT_HOST_THREADS")) nthreads = atoi(e);
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 64) nthreads = 64;
     for (int i = 0; i < nthreads; ++i) hx->workers.emplace_back(hx_worker, hx, h->device);
-    h->host_stats[0] += (double)hx->N * (sizeof(int32_t) + 7 * sizeof(double)) + (double)nwin * (double)(stage_bytes + rows_bytes);
+    h->host_stats[0] += (double)hx->N * (sizeof(int32_t) + 7 * sizeof(double));   // slot map + the t = 0 row; windows add theirs
     h->host_stats[2] = nwin;
     h->host_stats[3] = nthreads;
     return RWRT_OK;
 }
 
-// before window w's kernel: its device record buffer (w & 1) was last read by the copy of window w - 2
-static int hx_before_window(HostExpand *hx, int w, cudaStream_t s)
-{
-    if (w >= 2) CU(cudaStreamWaitEvent(s, hx->copied[w - 2], 0));
-    return RWRT_OK;
-}
-
-static int hx_on_window(HostExpand *hx, int w, int it_begin, int it_end, const double *rec_dev, int rec_rows,
+static int hx_on_window(HostExpand *hx, rwrt_handle h, int w, int it_begin, int it_end, const double *rec_dev, int rec_rows,
                         const int32_t *rows_done_dev, long long nlive, cudaStream_t s)
 {
     hx->w_begin[w] = it_begin;
     hx->w_end[w] = it_end;
     if (w >= HX_STAGES) {                       // the staging buffer is reused: wait for its previous window on the host
-        while ((*hx->chunks_done)[w - HX_STAGES].load(std::memory_order_acquire) < hx->nchunk) {
-            if (hx->abort.load()) return fail(RWRT_ERR_CUDA, "host expansion aborted");
-            std::this_thread::yield();
-        }
+        std::unique_lock<std::mutex> lk(hx->mu);
+        hx->cv.wait(lk, [&] { return (*hx->chunks_done)[w - HX_STAGES].load(std::memory_order_acquire) >= hx->nchunk || hx->abort.load(); });
+        if (hx->abort.load()) return fail(RWRT_ERR_CUDA, "host expansion aborted");
     }
-    CU(cudaEventRecord(hx->kernel_done[w], s));
-    CU(cudaStreamWaitEvent(hx->copy_stream, hx->kernel_done[w], 0));
-    // rows_done only grows, and a later window's kernel may already be raising it while this copy reads it: every
-    // value it can see marks the rows of window w of a ray that was alive at the end of window w as valid
-    CU(cudaMemcpyAsync(hx->rows_stage[w % HX_STAGES], rows_done_dev, (size_t)nlive * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                       hx->copy_stream));
-    CU(cudaMemcpyAsync(hx->stage[w % HX_STAGES], rec_dev, (size_t)nlive * rec_rows * 8 * sizeof(double), cudaMemcpyDeviceToHost,
-                       hx->copy_stream));
+    // records -> packed planes of the live rays (device buffer w & 1: last read by the copy of window w - 2)
+    double *packed = (double *)h->packed.p + (size_t)(w & 1) * (size_t)nlive * rec_rows * 7;
+    if (w >= 2) CU(cudaStreamWaitEvent(s, hx->copied[w - 2], 0));
+    launch_pack_records(rec_dev, rec_rows, rows_done_dev, nlive, it_begin, it_end, packed, s);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(hx->packed_ev[w], s));
+    CU(cudaStreamWaitEvent(hx->copy_stream, hx->packed_ev[w], 0));
+    const size_t bytes = (size_t)nlive * (size_t)(it_end - it_begin) * 7 * sizeof(double);
+    CU(cudaMemcpyAsync(hx->stage[w % HX_STAGES], packed, bytes, cudaMemcpyDeviceToHost, hx->copy_stream));
     CU(cudaEventRecord(hx->copied[w], hx->copy_stream));
-    hx->enqueued.store(w + 1, std::memory_order_release);
+    h->host_stats[0] += (double)bytes;
+    {
+        std::lock_guard<std::mutex> lk(hx->mu);
+        hx->enqueued.store(w + 1, std::memory_order_release);
+    }
+    hx->cv.notify_all();
     return RWRT_OK;
 }
 
 // joins the workers (after every window has been expanded when ok, at once otherwise) and frees the per-call objects
 static int hx_finish(HostExpand *hx, bool ok)
 {
-    if (!ok) hx->abort.store(true);
+    if (!ok) {
+        std::lock_guard<std::mutex> lk(hx->mu);
+        hx->abort.store(true);
+    }
+    hx->cv.notify_all();
     for (auto &t : hx->workers) t.join();
     hx->workers.clear();
-    for (auto e : hx->kernel_done) if (e) cudaEventDestroy(e);
+    for (auto e : hx->packed_ev) if (e) cudaEventDestroy(e);
     for (auto e : hx->copied) if (e) cudaEventDestroy(e);
-    hx->kernel_done.clear();
+    hx->packed_ev.clear();
     hx->copied.clear();
     delete hx->chunks_done;
     hx->chunks_done = nullptr;
     return hx->abort.load() ? RWRT_ERR_CUDA : RWRT_OK;
 }
 
-// Host half of rwrt_real2d_host on its own (tests, and callers that move the records themselves): rows [row_begin,
-// row_end) of slots [slot_begin, slot_end) of the seven planes from the records of one time window.  Pure host code.
-int rwrt_host_expand_rows(double *out7_host, int nt, int64_t nslot, const int32_t *slot_to_ray, const double *records,
-                          const int32_t *rows_done, int rec_rows, int row_begin, int row_end, int64_t slot_begin,
-                          int64_t slot_end)
+// Host half of rwrt_real2d_host on its own (tests, and callers that move the packed rows themselves): rows [row_begin,
+// row_end) of slots [slot_begin, slot_end) of the seven planes from the packed rows of one time window.  Pure host code.
+int rwrt_host_expand_rows(double *out7_host, int nt, int64_t nslot, const int32_t *slot_to_ray, const double *packed,
+                          int64_t nray, int row_begin, int row_end, int64_t slot_begin, int64_t slot_end)
 {
-    if (!out7_host || !slot_to_ray || !records || !rows_done || nt < 1 || nslot < 0 || rec_rows < 1 || row_begin < 1 ||
-        row_end > nt || row_end - row_begin > rec_rows || slot_begin < 0 || slot_end > nslot)
+    if (!out7_host || !slot_to_ray || !packed || nt < 1 || nslot < 0 || nray < 1 || row_begin < 1 || row_end > nt ||
+        slot_begin < 0 || slot_end > nslot)
         return fail(RWRT_ERR_ARG, "rwrt_host_expand_rows: bad argument");
     HxView v;
     v.out = out7_host;
     v.pl = (size_t)nt * (size_t)nslot;
     v.N = nslot;
     v.inv = slot_to_ray;
-    v.stage = records;
-    v.rows_done = rows_done;
-    v.rec_rows = rec_rows;
-    if (row_begin < row_end && slot_begin < slot_end) hx_expand_rows(v, row_begin, row_end, slot_begin, slot_end);
+    v.packed = packed;
+    v.nray = nray;
+    v.rows = row_end - row_begin;
+    if (v.rows > 0)
+        for (int64_t s0 = slot_begin; s0 < slot_end; s0 += HX_CHUNK)
+            hx_expand_rows(v, row_begin, s0, s0 + HX_CHUNK < slot_end ? s0 + HX_CHUNK : slot_end);
     return RWRT_OK;
 }
 
@@ -819,6 +882,7 @@ int rwrt_trim(rwrt_handle h)
     CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
     h->records.release();
+    h->packed.release();
     h->rows_done.release();
     h->inv.release();
     h->state.release();

@@ -56,4 +56,7 @@ int measure_fp64_peak(int sm_count, double *tflops, cudaStream_t s);
 void launch_compact_live(long long N, size_t plane_stride, const double *out7, int nsource, int nzwn, int32_t *live, int32_t *inv,
                          unsigned long long *nlive_dev, int *block_counts, int nblocks, cudaStream_t s);
 
+void launch_pack_records(const double *rec, int rec_rows, const int32_t *rows_done, long long nlive, int it_begin, int it_end,
+                         double *packed, cudaStream_t s);
+
 }  // namespace rwrt

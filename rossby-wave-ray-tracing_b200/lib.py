@@ -63,7 +63,7 @@ def load():
     L.rwrt_grid_accumulate.argtypes = [vp, i64, i32, vp, f64, f64, i32, i32, vp, vp, vp, vp]
     L.rwrt_real2d_host.argtypes = ([vp] + [vp] * 6 + [i32, vp, vp, vp, i32, vp, f64, i32] + [f64] * 6 +
                                    [u32, vp, vp, vp, vp, vp])
-    L.rwrt_host_expand_rows.argtypes = [vp, i32, i64, vp, vp, vp, i32, i32, i32, i64, i64]
+    L.rwrt_host_expand_rows.argtypes = [vp, i32, i64, vp, vp, i64, i32, i32, i64, i64]
     L.rwrt_last_run_stats.argtypes = [vp, C.POINTER(f64)]
     L.rwrt_last_host_stats.argtypes = [vp, C.POINTER(f64)]
     L.rwrt_measure_fp64_peak.argtypes = [vp, C.POINTER(f64)]

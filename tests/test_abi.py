@@ -104,45 +104,43 @@ def test_ncio_roundtrip(tmp_path):
     assert np.array_equal(d["lon"], (lon_deg * np.pi / 180).astype("float64"))
 
 
-def _expand_numpy(out, inv, rec, rows_done, b, e):
-    """Restatement of the record -> plane transpose (what expand_records does on the device; wr.py:768-781 for the
-    constant rows of no-root slots, wr.py:838-855 for the NaN tail of a dead ray)."""
+def _expand_numpy(out, inv, packed, b, e):
+    """Restatement of the packed rows -> plane expansion (wr.py:768-781 for the constant rows of no-root slots)."""
     for s, li in enumerate(inv):
         for it in range(b, e):
             if li < 0:
                 out[:5, it, s] = out[:5, 0, s]
                 out[5:, it, s] = np.nan
-            elif it < rows_done[li]:
-                out[:, it, s] = rec[li, it - b, :7]
             else:
-                out[:, it, s] = np.nan
+                out[:, it, s] = packed[:, it - b, li]
 
 
-@pytest.mark.parametrize("nslot,nt,b,e,rec_rows", [(1, 2, 1, 2, 1), (37, 9, 1, 9, 8), (301, 40, 17, 36, 20), (64, 20, 3, 19, 16),
-                                                    (1030, 7, 2, 6, 4)])
-def test_host_expand_rows_equals_restatement(L, nslot, nt, b, e, rec_rows):
+@pytest.mark.parametrize("isa", ["sse2", "avx2", "avx512"])
+@pytest.mark.parametrize("nslot,nt,b,e", [(1, 2, 1, 2), (37, 9, 1, 9), (301, 40, 17, 36), (64, 20, 3, 19), (1030, 7, 2, 6),
+                                          (9001, 4, 1, 3)])
+def test_host_expand_rows_equals_restatement(L, monkeypatch, isa, nslot, nt, b, e):
     """rwrt_host_expand_rows (the host half of rwrt_real2d_host; pure host code) against a NumPy restatement: ragged
-    slot counts (unaligned lines), no-root slots, rays that died before / inside / after the window, sub-ranges of
-    slots, untouched rows outside the window."""
+    slot counts (unaligned lines, every store width the CPU has), no-root slots, dead rays (NaN rows), sub-ranges of
+    slots longer than one task chunk, untouched rows outside the window."""
+    monkeypatch.setenv("RWRT_HX_ISA", isa)    # the library never picks a wider path than the CPU supports
     rng = np.random.default_rng(nslot * 1000 + nt)
     inv = np.full(nslot, -1, dtype=np.int32)
     live = rng.random(nslot) < 0.55
+    live[0] = True
     nlive = int(live.sum())
     inv[live] = rng.permutation(nlive).astype(np.int32)      # any slot -> ray map
-    rec = rng.standard_normal((max(nlive, 1), rec_rows, 8))
-    rows_done = rng.integers(1, nt + 3, size=max(nlive, 1)).astype(np.int32)
+    packed = rng.standard_normal((7, e - b, nlive))
+    packed[:, (e - b) // 2:, ::5] = np.nan                   # rays that died inside the window
     out = np.full((7, nt, nslot), -7.0)
     out[:, 0, :] = rng.standard_normal((7, nslot))
     out[3:5, 0, ~live] = np.nan
     want = out.copy()
-    _expand_numpy(want, inv, rec, rows_done, b, e)
+    _expand_numpy(want, inv, packed, b, e)
     # in two slot ranges, like two worker threads
     cut = nslot // 3
     for s0, s1 in ((0, cut), (cut, nslot)):
-        lib.check(L.rwrt_host_expand_rows(lib.ptr(out), nt, nslot, lib.ptr(inv), lib.ptr(rec), lib.ptr(rows_done), rec_rows, b, e,
-                                          s0, s1))
+        lib.check(L.rwrt_host_expand_rows(lib.ptr(out), nt, nslot, lib.ptr(inv), lib.ptr(packed), nlive, b, e, s0, s1))
     assert np.array_equal(out, want, equal_nan=True)
-    # argument errors: row 0 is not produced here; the window must fit the records
-    assert L.rwrt_host_expand_rows(lib.ptr(out), nt, nslot, lib.ptr(inv), lib.ptr(rec), lib.ptr(rows_done), rec_rows, 0, e, 0, nslot) != 0
-    assert L.rwrt_host_expand_rows(lib.ptr(out), nt, nslot, lib.ptr(inv), lib.ptr(rec), lib.ptr(rows_done), rec_rows, 1,
-                                   1 + rec_rows + 1, 0, nslot) != 0
+    # argument errors: row 0 is not produced here; rows must exist
+    assert L.rwrt_host_expand_rows(lib.ptr(out), nt, nslot, lib.ptr(inv), lib.ptr(packed), nlive, 0, e, 0, nslot) != 0
+    assert L.rwrt_host_expand_rows(lib.ptr(out), nt, nslot, lib.ptr(inv), lib.ptr(packed), nlive, 1, nt + 1, 0, nslot) != 0

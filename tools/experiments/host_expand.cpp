@@ -7,25 +7,23 @@
 #include <cstring>
 #include <thread>
 #include <vector>
-#include "../../rossby-wave-ray-tracing_b200/csrc/rwrt_hx.h"
+#include "../../rossby-wave-ray-tracing_b200/csrc/rwrt_hx.cpp"
 using namespace rwrt;
 int main(int argc, char **argv)
 {
     int T = argc > 1 ? atoi(argv[1]) : (int)std::thread::hardware_concurrency();
     const long long N = 1146960;
-    const int rows = 15, rec_rows = 16, nt = 1 + 4 * rows;     // 4 windows' worth of output rows
+    const int rows = 15, nt = 1 + 4 * rows;     // 4 windows' worth of output rows
     std::vector<int32_t> inv(N);
     long long nlive = 0;
     for (long long s = 0; s < N; ++s) inv[s] = ((s / 6) % 2) ? (int32_t)nlive++ : -1;   // half the slots are live, in runs
-    std::vector<int32_t> rd(nlive, 1 << 30);
-    for (long long i = 0; i < nlive; i += 37) rd[i] = 7;      // a few dead rays
-    double *stage = (double *)aligned_alloc(64, (size_t)nlive * rec_rows * 64);
-    for (size_t i = 0; i < (size_t)nlive * rec_rows * 8; ++i) stage[i] = (double)i;
+    double *stage = (double *)aligned_alloc(64, (size_t)7 * rows * nlive * 8);      // packed [7][rows][nlive]
+    for (size_t i = 0; i < (size_t)7 * rows * nlive; ++i) stage[i] = (double)i;
     const size_t pl = (size_t)nt * N;
     double *out = (double *)aligned_alloc(64, 7 * pl * 8);
     memset(out, 0, 7 * pl * 8);
-    HxView v{out, pl, N, inv.data(), stage, rd.data(), rec_rows};
-    const long long chunk = 4096;
+    HxView v{out, pl, N, inv.data(), stage, nlive, rows};
+    const long long chunk = HX_CHUNK;
     const int nchunk = (int)((N + chunk - 1) / chunk);
     double best = 1e9; for (int rep = 0; rep < 12; ++rep) {
         std::atomic<int> next{0};
@@ -38,12 +36,12 @@ int main(int argc, char **argv)
                     if (task >= 4 * nchunk) return;
                     int w = task / nchunk, c = task % nchunk;
                     long long s0 = c * chunk, s1 = s0 + chunk < N ? s0 + chunk : N;
-                    hx_expand_rows(v, 1 + w * rows, 1 + (w + 1) * rows, s0, s1);
+                    hx_expand_rows(v, 1 + w * rows, s0, s1);
                 }
             });
         for (auto &x : th) x.join();
         double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        double wr = 4.0 * rows * N * 7 * 8, rdb = 4.0 * rows * nlive * 64;
+        double wr = 4.0 * rows * N * 7 * 8, rdb = 4.0 * rows * nlive * 56;
         if (s < best) best = s; if (rep == 11) printf("%d threads: best %.1f ms for 4 windows, %.1f GB/s written + %.1f GB/s read\n", T, best * 1e3, wr / best / 1e9, rdb / best / 1e9);
     }
     return 0;
