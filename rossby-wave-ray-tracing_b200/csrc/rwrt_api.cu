@@ -85,7 +85,6 @@ struct rwrt_ctx {
     void *hx_stage[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t hx_stage_cap = 0;
     int hx_nstage = 0;
-    const double *hx_row0 = nullptr;    // device (7, N): the t = 0 state of the current host-expanded run
     double host_stats[4] = {0, 0, 0, 0};  // last rwrt_real2d_host: bytes D2H, bytes H2D, time windows, host threads
     void release_hx_staging()
     {
@@ -494,10 +493,37 @@ typedef int (*window_hook)(void *ctx, int it_begin, int it_end, cudaStream_t s);
 
 // Host-side expansion (rwrt_real2d_host): the ray records of every time window travel to the host instead of the
 // reference-layout rows (13 GB instead of 23 GB on C2) and host threads write the caller's arrays from them.
-struct HostExpand;
+constexpr int HX_STAGES = 4;
+struct HostExpand {
+    // set by the caller
+    double *out7_host = nullptr;            // (7, nt, N)
+    long long N = 0;
+    int nt = 0;
+    cudaStream_t copy_stream = nullptr;
+    bool row0_only = true;                  // the device holds only the t = 0 row (7, N); false: full planes (7, nt, N) that
+                                            // expand_records fills as well (rwrt_ray_run_rk45_d2h)
+    // filled by hx_begin
+    long long nlive = 0;
+    int rec_rows = 0, nwin = 0;
+    std::vector<int32_t> inv;               // slot -> live index (host copy)
+    double *stage[HX_STAGES] = {};          // pinned (owned by the handle): packed rows of one window, 7 x rows x nlive doubles
+    std::vector<cudaEvent_t> packed_ev, copied;     // per window
+    std::vector<int> w_begin, w_end;
+    std::atomic<int> enqueued{0};           // windows whose D2H has been queued
+    std::vector<std::atomic<int>> *chunks_done = nullptr;   // per window: finished chunks
+    int nchunk = 0;
+    long long chunk_slots = 0;
+    std::vector<std::thread> workers;
+    std::atomic<int> next_task{0};
+    std::atomic<bool> abort{false};
+    std::mutex mu;                          // waits (window queued / window expanded) sleep on cv instead of spinning:
+    std::condition_variable cv;             // the launching thread and the CUDA driver threads need the cores too
+};
+
 static int hx_on_window(HostExpand *hx, rwrt_handle h, int w, int it_begin, int it_end, const double *rec_dev, int rec_rows,
                         const int32_t *rows_done_dev, long long nlive, cudaStream_t s);
-static int hx_begin(HostExpand *hx, rwrt_handle h, long long nlive, int rec_rows, int nwin, cudaStream_t s);
+static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_t dev_pl, long long nlive, int rec_rows, int nwin,
+                    cudaStream_t s);
 #define RWRT_HX_UNSUPPORTED 12345   /* internal: the caller falls back to device-side expansion */
 
 static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
@@ -538,7 +564,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         const char *er = getenv("RWRT_RECORDS");
         use_records = !(er && atoi(er) == 0);
         if (use_records && h->inv.reserve((size_t)N * sizeof(int32_t))) return fail(RWRT_ERR_NOMEM, "slot map allocation failed");
-        launch_compact_live(N, hx ? (size_t)N : (size_t)nt * N, out7, slot_order ? (int)1 : nsource, slot_order ? (int)1 : nzwn, (int32_t *)h->live.p,
+        launch_compact_live(N, (hx && hx->row0_only) ? (size_t)N : (size_t)nt * N, out7, slot_order ? (int)1 : nsource, slot_order ? (int)1 : nzwn, (int32_t *)h->live.p,
                             use_records ? (int32_t *)h->inv.p : nullptr, ctr + 2, (int *)h->blockcnt.p, nblocks, s);
     }
     unsigned long long nlive = 0;
@@ -563,7 +589,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     p.gmin = fmin(min_step_factor * tstep, (tstep - 0) * 0.001);
     p.cut = cut_off * tstep / 3600.;
     p.out = out7;
-    p.out_pl = hx ? (size_t)N : (size_t)nt * N;
+    p.out_pl = (hx && hx->row0_only) ? (size_t)N : (size_t)nt * N;
     p.live = (const int32_t *)h->live.p;
     p.nlive = (long long)nlive;
     p.state = (double *)h->state.p;
@@ -624,7 +650,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         p.rows_done = (int32_t *)h->rows_done.p;
         p.inv = (const int32_t *)h->inv.p;
         if (hx) {
-            int rc = hx_begin(hx, h, (long long)nlive, rows, nwin, s);
+            int rc = hx_begin(hx, h, out7, p.out_pl, (long long)nlive, rows, nwin, s);
             if (rc) return rc;
         }
     }
@@ -647,10 +673,11 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         else launch_rk45_window_fast(p, integrate_blocks, s);
         CU(cudaGetLastError());
         ++launches;
-        if (hx) {
+        if (hx) {                                   // rows [it_begin, it_end) of the live rays as packed planes -> host
             int rc = hx_on_window(hx, h, w, p.it_begin, p.it_end, p.rec, p.rec_rows, p.rows_done, (long long)nlive, s);
             if (rc) return rc;
-        } else if (use_records) {                   // rows [it_begin, it_end) of the reference layout from the records
+        }
+        if (use_records && !(hx && hx->row0_only)) {   // rows [it_begin, it_end) of the reference layout from the records
             if (strict) launch_expand_records_strict(p, s);
             else launch_expand_records_fast(p, s);
             CU(cudaGetLastError());
@@ -672,38 +699,15 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
 
 
 // ---------------------------------------------------------------------------------------------
-// Host-side expansion of the ray records (rwrt_real2d_host).
+// Host-side expansion (rwrt_real2d_host, rwrt_ray_run_rk45_d2h).
 //
-// The link to the host is the bottleneck of the host-buffer call (23.2 GB of reference-layout rows per C2 pass at
-// 34-55 GB/s).  Half of those bytes are redundant: NaN-root slots are constant / NaN in every row, dead rays are NaN.
-// So the records (64 B per live ray and row: 13 GB) cross the link, window by window, into pinned staging buffers,
-// and host threads write the caller's seven arrays from them: 8 consecutive slots x 1 row = one 64-byte line per
-// plane, non-temporal stores.  Device buffers alternate between two windows, staging buffers between HX_STAGES.
+// The link to the host is the bottleneck of the host-buffer calls (23.2 GB of reference-layout rows per C2 pass at
+// 30-55 GB/s).  Half of those bytes are redundant: slots without a root are constant / NaN in every row.  So after
+// each time window pack_records turns the ray records into seven planes over the live rays (56 B per live ray and
+// row: 11.6 GB per C2 pass), those cross the link into pinned staging buffers while the next window integrates, and
+// host threads write the caller's seven arrays from them with non-temporal stores (rwrt_hx.cpp).  Two packed buffers
+// alternate on the device, HX_STAGES staging buffers on the host.
 // ---------------------------------------------------------------------------------------------
-constexpr int HX_STAGES = 4;
-struct HostExpand {
-    // set by the caller
-    double *out7_host = nullptr;            // (7, nt, N)
-    long long N = 0;
-    int nt = 0;
-    cudaStream_t copy_stream = nullptr;
-    // filled by hx_begin
-    long long nlive = 0;
-    int rec_rows = 0, nwin = 0;
-    std::vector<int32_t> inv;               // slot -> live index (host copy)
-    double *stage[HX_STAGES] = {};          // pinned (owned by the handle): packed rows of one window, 7 x rows x nlive doubles
-    std::vector<cudaEvent_t> packed_ev, copied;     // per window
-    std::vector<int> w_begin, w_end;
-    std::atomic<int> enqueued{0};           // windows whose D2H has been queued
-    std::vector<std::atomic<int>> *chunks_done = nullptr;   // per window: finished chunks
-    int nchunk = 0;
-    long long chunk_slots = 0;
-    std::vector<std::thread> workers;
-    std::atomic<int> next_task{0};
-    std::atomic<bool> abort{false};
-    std::mutex mu;                          // waits (window queued / window expanded) sleep on cv instead of spinning:
-    std::condition_variable cv;             // the launching thread and the CUDA driver threads need the cores too
-};
 
 static void hx_worker(HostExpand *hx, int device)
 {
@@ -744,7 +748,8 @@ static void hx_worker(HostExpand *hx, int device)
     }
 }
 
-static int hx_begin(HostExpand *hx, rwrt_handle h, long long nlive, int rec_rows, int nwin, cudaStream_t s)
+static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_t dev_pl, long long nlive, int rec_rows, int nwin,
+                    cudaStream_t s)
 {
     hx->nlive = nlive;
     hx->rec_rows = rec_rows;
@@ -753,7 +758,7 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, long long nlive, int rec_rows
     CU(cudaMemcpyAsync(hx->inv.data(), h->inv.p, (size_t)hx->N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     // row 0 (the t = 0 state, wr.py:768-781) goes to the caller's planes now: the workers read the constant values of
     // NaN-root slots from it
-    CU(cudaMemcpy2DAsync(hx->out7_host, (size_t)hx->nt * hx->N * sizeof(double), h->hx_row0, (size_t)hx->N * sizeof(double),
+    CU(cudaMemcpy2DAsync(hx->out7_host, (size_t)hx->nt * hx->N * sizeof(double), out7_dev, dev_pl * sizeof(double),
                          (size_t)hx->N * sizeof(double), 7, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     // pinned staging buffers live on the handle: pinning 2 GB costs more than a whole C2 pass
@@ -1015,29 +1020,54 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
     if (const char *e = getenv("RWRT_HOST_WINDOWS")) nwin = atoi(e);
     if (nwin < 1) nwin = 1;
     if (nwin > 64) nwin = 64;
-    HostCopyCtx ctx;
-    ctx.copy_stream = nullptr;
-    ctx.ev[0] = ctx.ev[1] = nullptr;
-    ctx.n_ev = 0;
-    ctx.dev = out7;
-    ctx.host = out7_host;
-    ctx.N = N;
-    ctx.nt = nt;
-    ctx.first = true;
-    CU(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&ctx.ev[0], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ctx.ev[1], cudaEventDisableTiming));
-    int rc = run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7,
-                      accepted, attempts, status, total_accepted, stream, nwin, host_copy_hook, &ctx);
-    if (rc == RWRT_OK && ctx.first && nout > 0 && out7) {
-        cudaError_t e = cudaMemcpyAsync(out7_host, out7, nout * 8, cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) rc = fail(RWRT_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    cudaStream_t copy_stream = nullptr;
+    CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    // Default: the device planes are filled as in rwrt_ray_run_rk45 and, beside them, the packed rows of the live rays
+    // travel to the host where threads write out7_host (see rwrt_real2d_host); RWRT_HOST_EXPAND=0 or a run without
+    // ray records: the finished rows of the device planes are copied as they are.
+    bool use_hx = nt >= 2 && N > 0 && out7;
+    if (const char *e = getenv("RWRT_HOST_EXPAND")) use_hx = use_hx && atoi(e) != 0;
+    int rc = RWRT_HX_UNSUPPORTED;
+    if (use_hx) {
+        HostExpand hx;
+        hx.out7_host = out7_host;
+        hx.N = N;
+        hx.nt = nt;
+        hx.copy_stream = copy_stream;
+        hx.row0_only = false;
+        rc = run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7,
+                      accepted, attempts, status, total_accepted, stream, nwin, nullptr, nullptr, &hx);
+        if (rc == RWRT_OK) {
+            if (cudaStreamSynchronize(s) != cudaSuccess || cudaStreamSynchronize(copy_stream) != cudaSuccess)
+                rc = fail(RWRT_ERR_CUDA, "rwrt_ray_run_rk45_d2h: stream synchronisation failed");
+        }
+        int rc2 = hx_finish(&hx, rc == RWRT_OK);
+        if (rc == RWRT_OK && rc2) rc = fail(rc2, "host-side expansion failed");
     }
-    cudaStreamSynchronize(s);
-    cudaStreamSynchronize(ctx.copy_stream);
-    cudaStreamDestroy(ctx.copy_stream);
-    cudaEventDestroy(ctx.ev[0]);
-    cudaEventDestroy(ctx.ev[1]);
+    if (rc == RWRT_HX_UNSUPPORTED) {
+        HostCopyCtx ctx;
+        ctx.copy_stream = copy_stream;
+        ctx.ev[0] = ctx.ev[1] = nullptr;
+        ctx.n_ev = 0;
+        ctx.dev = out7;
+        ctx.host = out7_host;
+        ctx.N = N;
+        ctx.nt = nt;
+        ctx.first = true;
+        CU(cudaEventCreateWithFlags(&ctx.ev[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx.ev[1], cudaEventDisableTiming));
+        rc = run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7,
+                      accepted, attempts, status, total_accepted, stream, nwin, host_copy_hook, &ctx);
+        if (rc == RWRT_OK && ctx.first && nout > 0 && out7) {
+            cudaError_t e = cudaMemcpyAsync(out7_host, out7, nout * 8, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = fail(RWRT_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+        }
+        cudaStreamSynchronize(s);
+        cudaStreamSynchronize(copy_stream);
+        cudaEventDestroy(ctx.ev[0]);
+        cudaEventDestroy(ctx.ev[1]);
+    }
+    cudaStreamDestroy(copy_stream);
     return rc;
 }
 
@@ -1130,7 +1160,6 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
         rc = rwrt_ray_init(h, nsource, (const double *)(arena + o_slon), (const double *)(arena + o_slat), dmem, nzwn,
                            (const double *)(arena + o_zwn), freq, use_hx ? 1 : nt, (double *)(arena + o_out), s);
         if (rc) goto done;
-        h->hx_row0 = (const double *)(arena + o_out);
         rc = run_rk45(h, nsource, dmem, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags,
                       (double *)(arena + o_out), (int64_t *)(arena + o_acc), nullptr, (int8_t *)(arena + o_st),
                       (int64_t *)(arena + o_tot), s, nwin, use_hx ? nullptr : host_copy_hook, &ctx, use_hx ? &hx : nullptr);
@@ -1148,7 +1177,6 @@ done:
         int rc2 = hx_finish(&hx, rc == RWRT_OK);    // joins the workers: every window is in the caller's arrays
         if (rc == RWRT_OK && rc2) rc = fail(rc2, "host-side expansion failed");
     }
-    h->hx_row0 = nullptr;
     if (ctx.copy_stream) {
         cudaStreamSynchronize(ctx.copy_stream);
         cudaStreamDestroy(ctx.copy_stream);

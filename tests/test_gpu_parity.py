@@ -221,6 +221,8 @@ def test_c_abi_host_entry_equals_facade(monkeypatch):
     days = 5.0
     w = make_wr(u, v, zwn, slon, slat, days)
     w.ray_run(mode="numpy", inte_method="rk45")
+    # the facade delivers through rwrt_ray_run_rk45_d2h: device planes and host planes of one run are the same bits
+    assert np.array_equal(w.d_out.cpu().numpy(), w._host_planes(), equal_nan=True)
     lon, lat = synthetic.grid_coords(144, 73)
     L = lib.load()
     nt = w.nt
