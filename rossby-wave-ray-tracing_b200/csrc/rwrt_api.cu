@@ -1,4 +1,5 @@
 // rwrt_api.cu -- the C ABI of librwrt.so (include/rwrt.h): handle, buffers, launch sequencing.
+#include <sched.h>
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
@@ -789,10 +790,18 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_
     for (auto &a : *hx->chunks_done) a.store(0);
     hx->chunk_slots = HX_CHUNK;                 // multiple of 8: 64-byte lines stay whole when N is a multiple of 8
     hx->nchunk = (int)((hx->N + hx->chunk_slots - 1) / hx->chunk_slots);
+    // worker threads: the cores this process may run on, shared between the ranks of a multi-GPU launch
     int nthreads = (int)std::thread::hardware_concurrency();
+    cpu_set_t cpus;
+    if (sched_getaffinity(0, sizeof cpus, &cpus) == 0 && CPU_COUNT(&cpus) > 0) nthreads = CPU_COUNT(&cpus);
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) {       // torchrun: ranks on this host
+        const int ranks = atoi(e);
+        if (ranks > 1) nthreads = (nthreads + ranks - 1) / ranks;
+    }
+    if (nthreads > 32) nthreads = 32;                       // the expansion is bound by memory bandwidth long before
     if (const char *e = getenv("RWRT_HOST_THREADS")) nthreads = atoi(e);
     if (nthreads < 1) nthreads = 1;
-    if (nthreads > 64) nthreads = 64;
+    if (nthreads > 256) nthreads = 256;
     for (int i = 0; i < nthreads; ++i) hx->workers.emplace_back(hx_worker, hx, h->device);
     h->host_stats[0] += (double)hx->N * (sizeof(int32_t) + 7 * sizeof(double));   // slot map + the t = 0 row; windows add theirs
     h->host_stats[2] = nwin;
