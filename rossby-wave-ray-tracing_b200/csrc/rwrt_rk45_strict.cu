@@ -16,7 +16,7 @@ void launch_expand_records_strict(const RunParams &p, cudaStream_t s)
 {
     int rows = p.it_end - p.it_begin;
     if (p.N > 0 && rows > 0)
-        strict::expand_records<<<dim3((unsigned)((p.N + strict::EX_SLOTS - 1) / strict::EX_SLOTS), (rows + strict::EX_ROWS - 1) / strict::EX_ROWS), 256, 0, s>>>(p);
+        strict::expand_records<<<dim3((unsigned)((p.N + strict::EX_SLOTS - 1) / strict::EX_SLOTS), (rows + strict::EX_ROWS_PER_BLOCK - 1) / strict::EX_ROWS_PER_BLOCK), 256, 0, s>>>(p);
 }
 
 // One time window [p.it_begin, p.it_end) of output rows for every live ray (the per-lane kernel has no
