@@ -650,10 +650,32 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         p.rec_rows = rows;
         p.rows_done = (int32_t *)h->rows_done.p;
         p.inv = (const int32_t *)h->inv.p;
-        if (hx) {
-            int rc = hx_begin(hx, h, out7, p.out_pl, (long long)nlive, rows, nwin, s);
-            if (rc) return rc;
+    }
+    // window bounds: rows [bounds[w], bounds[w + 1]) belong to window w.  Host delivery: the first and the last window
+    // are split (1/4, 1/4, 1/2) so that the pipeline fills and drains on quarter-size windows -- the host threads start
+    // after a quarter of a window has been integrated, packed and copied, and finish a quarter window after the last copy.
+    std::vector<int> bounds(nwin + 1);
+    for (int w = 0; w <= nwin; ++w) bounds[w] = 1 + (int)((long long)(nt - 1) * w / nwin);
+    if (hx && use_records) {
+        bool ramp = true;
+        if (const char *e = getenv("RWRT_HOST_RAMP")) ramp = atoi(e) != 0;
+        if (ramp && nwin >= 2) {
+            std::vector<int> b2;
+            auto split = [&](int b, int e, bool head) {
+                const int len = e - b, q = len / 4;
+                if (q < 1) { b2.push_back(b); return; }
+                if (head) { b2.push_back(b); b2.push_back(b + q); b2.push_back(b + 2 * q); }
+                else { b2.push_back(b); b2.push_back(e - 2 * q); b2.push_back(e - q); }
+            };
+            split(bounds[0], bounds[1], true);
+            for (int w = 1; w + 1 < nwin; ++w) b2.push_back(bounds[w]);
+            split(bounds[nwin - 1], bounds[nwin], false);
+            b2.push_back(bounds[nwin]);
+            bounds.swap(b2);
+            nwin = (int)bounds.size() - 1;
         }
+        int rc = hx_begin(hx, h, out7, p.out_pl, (long long)nlive, p.rec_rows, nwin, s);
+        if (rc) return rc;
     }
     CU(cudaEventRecord(h->ev0, s));
     CU(cudaEventRecord(h->ev_fork, s));            // fork: the side stream starts after everything queued so far
@@ -667,8 +689,8 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     CU(cudaStreamWaitEvent(s, h->ev_join, 0));     // join: the pre-fill (all rows >= 1) precedes the integrator's writes
     int launches = 0;
     for (int w = 0; w < nwin; ++w) {
-        p.it_begin = 1 + (int)((long long)(nt - 1) * w / nwin);
-        p.it_end = 1 + (int)((long long)(nt - 1) * (w + 1) / nwin);
+        p.it_begin = bounds[w];
+        p.it_end = bounds[w + 1];
         if (w > 0) CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));  // rewind the work queue
         if (strict) launch_rk45_window_strict(p, integrate_blocks, s);
         else launch_rk45_window_fast(p, integrate_blocks, s);
