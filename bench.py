@@ -416,7 +416,7 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
     hs = (C.c_double * 4)()
     lib.check(L.rwrt_last_host_stats(h, hs), "rwrt_last_host_stats")   # bytes the library actually moved in the last call
     if hs[3] > 0:
-        how = (f"ray records cross the link in {int(hs[2])} time windows, {int(hs[3])} host threads write the "
+        how = (f"packed rows of the live rays cross the link in {int(hs[2])} time windows, {int(hs[3])} host threads write the "
                f"{nbytes/1e9:.1f} GB of result planes")
     else:
         how = f"device-expanded rows cross the link in {int(hs[2])} time windows"
