@@ -54,18 +54,29 @@ class WR:
         self.status = None           # (3, nsource, nzwn) int8, lib.RAY_*
         self.total_accepted = 0
         self._host = None
+        self._host_t = None
+        self.pin_results = False     # result planes in pinned host memory (see _host_planes)
 
     # ---- result arrays: allocated on first use (the reference allocates them in __init__) ----
-    def _host_planes(self):
+    def _host_planes(self, fill=True):
+        """The seven result planes on the host.  Pageable NumPy memory by default: the delivery from the GPU writes it
+        with host threads (rwrt_ray_run_rk45_d2h), so pinning 23 GB (seconds) buys nothing; `pin_results = True`
+        before the first use gives pinned memory (faster `to_host()` after the RK4 path or repeated runs).
+        fill=False skips the NaN pre-fill of wr.py:160-167 when a run is about to overwrite every element."""
         if self._host is None:
             shape = (7, self.nt, 3, self.nsource, self.nzwn)
-            try:
-                import torch
-                self._host_t = torch.empty(shape, dtype=torch.float64, pin_memory=torch.cuda.is_available())
-                self._host = self._host_t.numpy()
-            except Exception:
+            self._host_t = None
+            if self.pin_results:
+                try:
+                    import torch
+                    self._host_t = torch.empty(shape, dtype=torch.float64, pin_memory=torch.cuda.is_available())
+                    self._host = self._host_t.numpy()
+                except Exception:
+                    self._host_t = None
+            if self._host_t is None:
                 self._host = np.empty(shape, dtype=np.float64)
-            self._host.fill(undef)                                       # wr.py:160-167
+            if fill:
+                self._host.fill(undef)                                   # wr.py:160-167
         return self._host
 
     def __getattr__(self, name):
@@ -161,8 +172,8 @@ class WR:
                 float(self.rtol), float(self.atol), float(self.MinStepFactor), float(self.cut_off_factor), flags,
                 _lib.ptr(self.d_out), _lib.ptr(self._d_acc), None, _lib.ptr(self._d_status), _lib.ptr(self._d_total))
         with torch.cuda.device(self.bs.device):
-            if to_host and hasattr(self, "_host_t") and N > 0:
-                _lib.check(_lib.load().rwrt_ray_run_rk45_d2h(*args, _lib.ptr(self._host_t), _lib.stream_ptr()),
+            if to_host and self._host is not None and N > 0:
+                _lib.check(_lib.load().rwrt_ray_run_rk45_d2h(*args, _lib.ptr(self._host), _lib.stream_ptr()),
                            "rwrt_ray_run_rk45_d2h")
                 return True
             _lib.check(_lib.load().rwrt_ray_run_rk45(*args, _lib.stream_ptr()), "rwrt_ray_run_rk45")
@@ -196,9 +207,14 @@ class WR:
         shp = (3, self.nsource, self.nzwn)
         if inte_method == "rk45":                                       # wr.py:907-908
             if to_host:
-                self._host_planes()          # the (pinned) result arrays exist before the run
-            delivered = self.core_ray_run("numpy_rk45", strict=strict, to_host=to_host)
-            torch.cuda.synchronize(self.bs.device)
+                self._host_planes(fill=False)    # the result arrays exist before the run, which writes every element
+            try:
+                delivered = self.core_ray_run("numpy_rk45", strict=strict, to_host=to_host)
+                torch.cuda.synchronize(self.bs.device)
+            except Exception:
+                if self._host is not None:
+                    self._host.fill(undef)       # a failed run leaves "not propagating" everywhere, like wr.py:160-167
+                raise
             self.total_accepted = int(self._d_total.item())
             self.accepted = self._d_acc.cpu().numpy().reshape(shp)
         else:
@@ -214,12 +230,10 @@ class WR:
     def to_host(self):
         """Copy the seven result planes from the GPU into the (pinned) NumPy arrays."""
         import torch
-        host = self._host_planes()
-        if hasattr(self, "_host_t"):
-            self._host_t.copy_(self.d_out, non_blocking=True)
-            torch.cuda.synchronize(self.bs.device)
-        else:
-            host[...] = self.d_out.cpu().numpy()
+        host = self._host_planes(fill=False)
+        dst = self._host_t if self._host_t is not None else torch.from_numpy(host)
+        dst.copy_(self.d_out, non_blocking=self._host_t is not None)
+        torch.cuda.synchronize(self.bs.device)
         return host
 
     def output(self, ncfile):
@@ -232,6 +246,7 @@ class WR:
         self.bs.clean()
         self.d_out = None
         self._host = None
+        self._host_t = None
         for attr in ("source_lon", "source_lat", "zwn"):
             if hasattr(self, attr):
                 delattr(self, attr)
