@@ -1039,6 +1039,8 @@ int rwrt_ray_run_rk4(rwrt_handle h, int nsource, const int32_t *src_member, int 
     return RWRT_OK;
 }
 
+static int host_windows_default(size_t nout_doubles) { return (int)((nout_doubles * sizeof(double)) >> 29); }
+
 int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
                           double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
                           double *out7, int64_t *accepted, int64_t *attempts, int8_t *status, int64_t *total_accepted,
@@ -1049,7 +1051,7 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
     CU(cudaSetDevice(h->device));
     const long long N = 3LL * nsource * nzwn;
     const size_t nout = (size_t)7 * nt * N;
-    int nwin = (int)((nout * sizeof(double)) >> 30);
+    int nwin = host_windows_default(nout);
     if (const char *e = getenv("RWRT_HOST_WINDOWS")) nwin = atoi(e);
     if (nwin < 1) nwin = 1;
     if (nwin > 64) nwin = 64;
@@ -1118,8 +1120,10 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
     const size_t nout = (size_t)7 * nt * N;
     // The integration runs in time windows; what a finished window produced travels to the host on a second stream
     // while the next window integrates.
-    int nwin = (int)((nout * sizeof(double)) >> 30);  // ~1 GB of trajectories per window (measured on C2: 1 / 4 / 10 / 24
-                                                      // windows -> 683 / 631 / 548 / 492 ms per pass on the same box)
+    // ~0.5 GB of result planes per window (device-expanded rows on C2, v9: 1 / 4 / 10 / 24 windows -> 683 / 631 / 548 /
+    // 492 ms per pass on the same box; packed rows, v16: 10 / 21 / 30 / 40 windows -> 326 / 305 / 312 / 300 ms).  Small
+    // windows also keep the pinned staging buffers small (4 x 0.14 GB on C2): pinning is what a one-shot call pays for.
+    int nwin = host_windows_default(nout);
     if (const char *e = getenv("RWRT_HOST_WINDOWS")) nwin = atoi(e);
     if (nwin < 1) nwin = 1;
     if (nwin > 64) nwin = 64;
