@@ -133,9 +133,11 @@ int rwrt_ray_run_rk4(rwrt_handle h, int nsource, const int32_t *src_member, int 
 
 /*
  * Same as rwrt_ray_run_rk45, and additionally delivers the seven result planes to HOST memory
- * out7_host (7, nt, 3, nsource, nzwn) -- pinned memory (rwrt_host_alloc) makes it asynchronous: the
- * integration runs in time windows and the finished rows of a window are copied while the next one
- * integrates.  out7 is the device buffer (row 0 = initial state, as above).  Synchronises before returning.
+ * out7_host (7, nt, 3, nsource, nzwn), pageable or pinned: the integration runs in time windows and what a
+ * finished window produced travels while the next one integrates -- by default as packed rows of the live rays that
+ * host threads expand into out7_host (see rwrt_real2d_host; RWRT_HOST_EXPAND=0: the finished rows of the device
+ * planes are copied as they are, fast only into pinned memory).  out7 is the device buffer (row 0 = initial state,
+ * as above) and holds the complete planes afterwards.  Synchronises before returning.
  */
 int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
                           double ttotal, double rtol, double atol, double min_step_factor, double cut_off,
