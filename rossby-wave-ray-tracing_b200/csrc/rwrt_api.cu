@@ -826,7 +826,12 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_
     if (const char *e = getenv("RWRT_HOST_THREADS")) nthreads = atoi(e);
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
-    for (int i = 0; i < nthreads; ++i) hx->workers.emplace_back(hx_worker, hx, h->device);
+    try {
+        for (int i = 0; i < nthreads; ++i) hx->workers.emplace_back(hx_worker, hx, h->device);
+    } catch (...) {     // thread limit of the process: go on with the threads that exist
+        if (hx->workers.empty()) return fail(RWRT_ERR_NOMEM, "could not start a host thread for the result expansion");
+        nthreads = (int)hx->workers.size();
+    }
     h->host_stats[0] += (double)hx->N * (sizeof(int32_t) + 7 * sizeof(double));   // slot map + the t = 0 row; windows add theirs
     h->host_stats[2] = nwin;
     h->host_stats[3] = nthreads;
