@@ -399,11 +399,14 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    reps = max(1, min(a.steps, 3))
+    reps = max(1, min(a.steps, 8))
     t0 = time.perf_counter()
     steps = 0
+    per_rep = []
     for _ in range(reps):
+        t_rep = time.perf_counter()
         call()                               # synchronises before returning
+        per_rep.append(round(1e3 * (time.perf_counter() - t_rep), 1))
         steps += int(tot_h.item())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
@@ -422,6 +425,7 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
         how = f"device-expanded rows cross the link in {int(hs[2])} time windows"
     return {"value": float(s.item()) / float(t.item()), "unit": "steps/s", "h2d_bytes_per_step": int(hs[1]),
             "d2h_bytes_per_step": int(hs[0]), "result_bytes_per_step": d2h, "ms_per_step": 1e3 * float(t.item()) / reps,
+            "ms_per_call": per_rep,          # this rank's calls (the value is total steps / total time, max over ranks)
             "api": "rwrt_real2d_host (C ABI, host pointers; pinned inputs and result arrays)", "transfer": how}
 
 
