@@ -416,11 +416,11 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     import ctypes as C
-    hs = (C.c_double * 4)()
+    hs = (C.c_double * 5)()
     lib.check(L.rwrt_last_host_stats(h, hs), "rwrt_last_host_stats")   # bytes the library actually moved in the last call
     if hs[3] > 0:
-        how = (f"packed rows of the live rays cross the link in {int(hs[2])} time windows, {int(hs[3])} host threads write the "
-               f"{nbytes/1e9:.1f} GB of result planes")
+        how = (f"{int(hs[2])} time windows: {int(hs[2] - hs[4])} as packed rows of the live rays that {int(hs[3])} host threads expand into "
+               f"the {nbytes/1e9:.1f} GB of result planes, {int(hs[4])} as device-expanded rows copied straight into them (last call)")
     else:
         how = f"device-expanded rows cross the link in {int(hs[2])} time windows"
     return {"value": float(s.item()) / float(t.item()), "unit": "steps/s", "h2d_bytes_per_step": int(hs[1]),

@@ -163,7 +163,9 @@ int rwrt_grid_accumulate(rwrt_handle h, int64_t nslot, int nt, const double *out
  * the LIVE rays (56 bytes per live ray and row) to pinned staging buffers kept on the handle while the next window
  * integrates, and host threads (RWRT_HOST_THREADS, default: all cores) write the caller's planes from them -- about
  * half of the reference-layout bytes are NaN / constant rows that never need to cross the link, and out7_host may
- * be pageable.  RWRT_HOST_EXPAND=0: the device
+ * be pageable.  When out7_host is pinned and all staging buffers are still waiting for the host threads (the cores, not
+ * the link, are the bottleneck), a window's device-expanded rows are copied straight into out7_host instead
+ * (RWRT_HOST_ROUTE=hx never does that, =direct always).  RWRT_HOST_EXPAND=0: the device
  * expands the records and the reference-layout rows travel (fast only into pinned memory, rwrt_host_alloc).
  * Both forms give the same bits.
  */
@@ -194,8 +196,9 @@ int rwrt_trim(rwrt_handle h);
 int rwrt_last_run_stats(rwrt_handle h, double *stats3);
 
 /* the last rwrt_real2d_host on this handle: [0] bytes copied device -> host, [1] bytes host -> device, [2] time windows,
- * [3] host threads that wrote the result planes (0: the device expanded them) */
-int rwrt_last_host_stats(rwrt_handle h, double *stats4);
+ * [3] host threads that wrote result planes (0: the device expanded all of them), [4] windows whose device-expanded rows
+ * were copied straight into the caller's pinned planes */
+int rwrt_last_host_stats(rwrt_handle h, double *stats5);
 
 /* Roofline denominator: measured FP64 FMA throughput of the device (TFLOP/s, register-resident DFMA
  * chains).  Diagnostic only; used by bench.py next to MEASURED_PEAKS.json, which has no FP64 figure. */

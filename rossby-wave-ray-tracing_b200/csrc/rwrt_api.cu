@@ -77,7 +77,7 @@ struct rwrt_ctx {
     int sm_count = 0;
     bool ready = false;
     double lon0 = 0, dlon = 0, lat0 = 0, dlat = 0;
-    DevBuf fpk, scratch, trig, live, state, counters, blockcnt, inv, rows_done, records, packed;
+    DevBuf fpk, scratch, trig, live, state, counters, blockcnt, inv, rows_done, records, packed, direct;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t aux = nullptr;  // side stream for work that is independent of the integrator
     bool timed = false;
@@ -86,7 +86,7 @@ struct rwrt_ctx {
     void *hx_stage[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t hx_stage_cap = 0;
     int hx_nstage = 0;
-    double host_stats[4] = {0, 0, 0, 0};  // last rwrt_real2d_host: bytes D2H, bytes H2D, time windows, host threads
+    double host_stats[5] = {0, 0, 0, 0, 0};  // last host-buffer call: bytes D2H, bytes H2D, time windows, host threads, direct windows
     void release_hx_staging()
     {
         for (int i = 0; i < 4; ++i) {
@@ -360,6 +360,7 @@ int rwrt_destroy(rwrt_handle h)
     h->rows_done.release();
     h->records.release();
     h->packed.release();
+    h->direct.release();
     h->scratch.release();
     h->trig.release();
     h->live.release();
@@ -503,6 +504,8 @@ struct HostExpand {
     cudaStream_t copy_stream = nullptr;
     bool row0_only = true;                  // the device holds only the t = 0 row (7, N); false: full planes (7, nt, N) that
                                             // expand_records fills as well (rwrt_ray_run_rk45_d2h)
+    int route_mode = 0;                     // 0 auto, 1 always through the host threads, 2 always direct, 3 alternate (tests)
+    bool can_direct = false;                // out7_host is pinned: a window's expanded rows may be copied straight into it
     // filled by hx_begin
     long long nlive = 0;
     int rec_rows = 0, nwin = 0;
@@ -510,6 +513,10 @@ struct HostExpand {
     double *stage[HX_STAGES] = {};          // pinned (owned by the handle): packed rows of one window, 7 x rows x nlive doubles
     std::vector<cudaEvent_t> packed_ev, copied;     // per window
     std::vector<int> w_begin, w_end;
+    std::vector<int> route, stage_of;       // per window: 1 = direct copy of device-expanded rows; staging buffer of a host window
+    std::vector<int> hx_windows;            // the windows that went through the host threads, in order
+    std::atomic<int> hx_finished{0};        // ... and how many of them are completely in the caller's arrays
+    int direct_count = 0, direct_last[2] = {-1, -1};   // direct windows so far; last window that used direct buffer 0 / 1
     std::atomic<int> enqueued{0};           // windows whose D2H has been queued
     std::vector<std::atomic<int>> *chunks_done = nullptr;   // per window: finished chunks
     int nchunk = 0;
@@ -521,8 +528,7 @@ struct HostExpand {
     std::condition_variable cv;             // the launching thread and the CUDA driver threads need the cores too
 };
 
-static int hx_on_window(HostExpand *hx, rwrt_handle h, int w, int it_begin, int it_end, const double *rec_dev, int rec_rows,
-                        const int32_t *rows_done_dev, long long nlive, cudaStream_t s);
+static int hx_on_window(HostExpand *hx, rwrt_handle h, int w, const RunParams &p, bool strict, const double *out7_dev, cudaStream_t s);
 static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_t dev_pl, long long nlive, int rec_rows, int nwin,
                     cudaStream_t s);
 #define RWRT_HX_UNSUPPORTED 12345   /* internal: the caller falls back to device-side expansion */
@@ -591,6 +597,9 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     p.cut = cut_off * tstep / 3600.;
     p.out = out7;
     p.out_pl = (hx && hx->row0_only) ? (size_t)N : (size_t)nt * N;
+    p.dst = out7;                                   // expand_records writes the planes themselves ...
+    p.dst_pl = (size_t)nt * N;                      // (... except for a direct window of rwrt_real2d_host, see hx_on_window)
+    p.dst_it0 = 0;
     p.live = (const int32_t *)h->live.p;
     p.nlive = (long long)nlive;
     p.state = (double *)h->state.p;
@@ -629,7 +638,10 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     if (nwin > nt - 1) nwin = nt - 1;
     if (use_records) {
         // the records of one time window must fit beside everything else: more windows when memory is short
-        const size_t per_row = (size_t)nlive * (8 + (hx ? 14 : 0)) * sizeof(double);   // host path: + two packed window buffers (7 doubles per row each)
+        // host path: + two packed window buffers (7 doubles per live ray and row each) and, when windows may be copied
+        // straight into pinned caller memory while only the t = 0 row lives on the device, two window buffers of expanded rows
+        const bool direct_bufs = hx && hx->row0_only && hx->can_direct;
+        const size_t per_row = (size_t)nlive * (8 + (hx ? 14 : 0)) * sizeof(double) + (direct_bufs ? (size_t)N * 14 * sizeof(double) : 0);
         size_t budget = h->records.cap;             // a buffer from an earlier call is reused as it is ...
         if (budget < per_row * (size_t)((nt - 1 + nwin - 1) / nwin + 1)) {   // ... unless it is too small (cudaMemGetInfo costs ms)
             size_t free_b = 0, total_b = 0;
@@ -644,7 +656,8 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         if (nwin > nt - 1) nwin = nt - 1;
         int rows = (nt - 1 + nwin - 1) / nwin + (hx ? 0 : 1);  // rows of the largest window (the host path copies whole buffers: no slack row)
         if (h->records.reserve((size_t)nlive * rows * 8 * sizeof(double)) || h->rows_done.reserve((size_t)nlive * sizeof(int32_t)) ||
-            (hx && h->packed.reserve((size_t)nlive * rows * 14 * sizeof(double))))
+            (hx && h->packed.reserve((size_t)nlive * rows * 14 * sizeof(double))) ||
+            (direct_bufs && h->direct.reserve((size_t)N * rows * 14 * sizeof(double))))
             return fail(RWRT_ERR_NOMEM, "record buffer allocation failed (%llu rays x %d rows x 64 B)", nlive, rows);
         p.rec = (double *)h->records.p;
         p.rec_rows = rows;
@@ -696,15 +709,15 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         else launch_rk45_window_fast(p, integrate_blocks, s);
         CU(cudaGetLastError());
         ++launches;
-        if (hx) {                                   // rows [it_begin, it_end) of the live rays as packed planes -> host
-            int rc = hx_on_window(hx, h, w, p.it_begin, p.it_end, p.rec, p.rec_rows, p.rows_done, (long long)nlive, s);
-            if (rc) return rc;
-        }
         if (use_records && !(hx && hx->row0_only)) {   // rows [it_begin, it_end) of the reference layout from the records
             if (strict) launch_expand_records_strict(p, s);
             else launch_expand_records_fast(p, s);
             CU(cudaGetLastError());
             ++launches;
+        }
+        if (hx) {                                   // rows [it_begin, it_end) -> host (packed planes of the live rays, or direct)
+            int rc = hx_on_window(hx, h, w, p, strict, out7, s);
+            if (rc) return rc;
         }
         if (hook) {
             int rc = hook(hook_ctx, p.it_begin, p.it_end, s);
@@ -745,6 +758,7 @@ static void hx_worker(HostExpand *hx, int device)
             hx->cv.wait(lk, [&] { return hx->enqueued.load(std::memory_order_acquire) > w || hx->abort.load(); });
         }
         if (hx->abort.load()) return;
+        if (hx->route[w]) continue;                                     // a direct window: the DMA engine writes it
         if (cudaEventSynchronize(hx->copied[w]) != cudaSuccess) {
             {
                 std::lock_guard<std::mutex> lk(hx->mu);
@@ -760,12 +774,13 @@ static void hx_worker(HostExpand *hx, int device)
         v.pl = (size_t)hx->nt * hx->N;
         v.N = hx->N;
         v.inv = hx->inv.data();
-        v.packed = hx->stage[w % HX_STAGES];
+        v.packed = hx->stage[hx->stage_of[w]];
         v.nray = hx->nlive;
         v.rows = hx->w_end[w] - hx->w_begin[w];
         hx_expand_rows(v, hx->w_begin[w], s0, s1);
         if ((*hx->chunks_done)[w].fetch_add(1, std::memory_order_acq_rel) + 1 == hx->nchunk) {   // window w is in the caller's arrays
             std::lock_guard<std::mutex> lk(hx->mu);
+            hx->hx_finished.fetch_add(1, std::memory_order_release);
             hx->cv.notify_all();
         }
     }
@@ -804,6 +819,9 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_
     hx->copied.assign(nwin, nullptr);
     hx->w_begin.assign(nwin, 0);
     hx->w_end.assign(nwin, 0);
+    hx->route.assign(nwin, 0);
+    hx->stage_of.assign(nwin, 0);
+    hx->hx_windows.clear();
     for (int w = 0; w < nwin; ++w) {
         CU(cudaEventCreateWithFlags(&hx->packed_ev[w], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&hx->copied[w], cudaEventDisableTiming | cudaEventBlockingSync));
@@ -838,25 +856,77 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_
     return RWRT_OK;
 }
 
-static int hx_on_window(HostExpand *hx, rwrt_handle h, int w, int it_begin, int it_end, const double *rec_dev, int rec_rows,
-                        const int32_t *rows_done_dev, long long nlive, cudaStream_t s)
+// Window w has been integrated (and, when the device holds the full planes, expanded).  Two ways to the host:
+//   host route   pack_records -> one copy of the packed planes of the live rays into a pinned staging buffer -> the
+//                worker threads write the caller's planes (half the link bytes, costs host cores and memory bandwidth);
+//   direct route the expanded rows of the window are copied straight into the caller's (pinned) planes by the DMA engine
+//                (twice the link bytes, no host work).
+// Default: the host route, and the direct route whenever all HX_STAGES staging buffers are still waiting for the host
+// threads -- i.e. when the cores, not the link, are what the delivery is waiting for.  Decisions are taken with at most
+// two copies outstanding, so that they see the current backlog.
+static int hx_on_window(HostExpand *hx, rwrt_handle h, int w, const RunParams &p, bool strict, const double *out7_dev, cudaStream_t s)
 {
+    const int it_begin = p.it_begin, it_end = p.it_end, len = it_end - it_begin;
+    const long long nlive = p.nlive, N = hx->N;
     hx->w_begin[w] = it_begin;
     hx->w_end[w] = it_end;
-    if (w >= HX_STAGES) {                       // the staging buffer is reused: wait for its previous window on the host
-        std::unique_lock<std::mutex> lk(hx->mu);
-        hx->cv.wait(lk, [&] { return (*hx->chunks_done)[w - HX_STAGES].load(std::memory_order_acquire) >= hx->nchunk || hx->abort.load(); });
-        if (hx->abort.load()) return fail(RWRT_ERR_CUDA, "host expansion aborted");
-    }
-    // records -> packed planes of the live rays (device buffer w & 1: last read by the copy of window w - 2)
-    double *packed = (double *)h->packed.p + (size_t)(w & 1) * (size_t)nlive * rec_rows * 7;
+    // records -> packed planes of the live rays (device buffer w & 1: last read by the copy of window w - 2); queued
+    // before the route is known so that the link never waits for it (0.15 ms of GPU time if the window goes direct)
+    double *packed = (double *)h->packed.p + (size_t)(w & 1) * (size_t)nlive * p.rec_rows * 7;
     if (w >= 2) CU(cudaStreamWaitEvent(s, hx->copied[w - 2], 0));
-    launch_pack_records(rec_dev, rec_rows, rows_done_dev, nlive, it_begin, it_end, packed, s);
+    launch_pack_records(p.rec, p.rec_rows, p.rows_done, nlive, it_begin, it_end, packed, s);
     CU(cudaGetLastError());
     CU(cudaEventRecord(hx->packed_ev[w], s));
-    CU(cudaStreamWaitEvent(hx->copy_stream, hx->packed_ev[w], 0));
-    const size_t bytes = (size_t)nlive * (size_t)(it_end - it_begin) * 7 * sizeof(double);
-    CU(cudaMemcpyAsync(hx->stage[w % HX_STAGES], packed, bytes, cudaMemcpyDeviceToHost, hx->copy_stream));
+    if (w >= 2) CU(cudaEventSynchronize(hx->copied[w - 2]));           // at most two copies in flight when the route is chosen
+    const int nhx = (int)hx->hx_windows.size();
+    bool direct = false;
+    if (hx->can_direct) {
+        const int backlog = nhx - hx->hx_finished.load(std::memory_order_acquire);
+        direct = hx->route_mode == 2 || (hx->route_mode == 3 && (w & 1)) || (hx->route_mode == 0 && backlog >= HX_STAGES);
+    }
+    size_t bytes;
+    if (!direct) {
+        if (nhx >= HX_STAGES) {                  // the staging buffer is reused: wait for its previous window on the host
+            const int prev = hx->hx_windows[nhx - HX_STAGES];
+            std::unique_lock<std::mutex> lk(hx->mu);
+            hx->cv.wait(lk, [&] { return (*hx->chunks_done)[prev].load(std::memory_order_acquire) >= hx->nchunk || hx->abort.load(); });
+            if (hx->abort.load()) return fail(RWRT_ERR_CUDA, "host expansion aborted");
+        }
+        hx->stage_of[w] = nhx % HX_STAGES;
+        hx->hx_windows.push_back(w);
+        bytes = (size_t)nlive * (size_t)len * 7 * sizeof(double);
+        CU(cudaStreamWaitEvent(hx->copy_stream, hx->packed_ev[w], 0));
+        CU(cudaMemcpyAsync(hx->stage[hx->stage_of[w]], packed, bytes, cudaMemcpyDeviceToHost, hx->copy_stream));
+    } else {
+        const double *src = out7_dev;            // full planes on the device: rows [it_begin, it_end) are final after expand_records
+        size_t src_pl = (size_t)hx->nt * N, src_row0 = (size_t)it_begin;
+        cudaEvent_t ready = hx->packed_ev[w];    // recorded after expand_records of this window (stream order)
+        if (hx->row0_only) {                     // only the t = 0 row lives on the device: expand this window into a buffer of its own
+            const int b = hx->direct_count & 1;
+            double *buf = (double *)h->direct.p + (size_t)b * (size_t)N * p.rec_rows * 7;
+            if (hx->direct_last[b] >= 0) CU(cudaStreamWaitEvent(s, hx->copied[hx->direct_last[b]], 0));
+            RunParams q = p;
+            q.dst = buf;
+            q.dst_pl = (size_t)N * len;
+            q.dst_it0 = it_begin;
+            if (strict) launch_expand_records_strict(q, s);
+            else launch_expand_records_fast(q, s);
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(hx->packed_ev[w], s));                   // re-recorded: now also after the expansion
+            hx->direct_last[b] = w;
+            ++hx->direct_count;
+            src = buf;
+            src_pl = (size_t)N * len;
+            src_row0 = 0;
+        }
+        CU(cudaStreamWaitEvent(hx->copy_stream, ready, 0));
+        bytes = (size_t)N * (size_t)len * 7 * sizeof(double);
+        for (int pl = 0; pl < 7; ++pl)
+            CU(cudaMemcpyAsync(hx->out7_host + ((size_t)pl * hx->nt + it_begin) * (size_t)N, src + pl * src_pl + src_row0 * (size_t)N,
+                               (size_t)N * len * sizeof(double), cudaMemcpyDeviceToHost, hx->copy_stream));
+        hx->route[w] = 1;
+        h->host_stats[4] += 1;
+    }
     CU(cudaEventRecord(hx->copied[w], hx->copy_stream));
     h->host_stats[0] += (double)bytes;
     {
@@ -926,6 +996,7 @@ int rwrt_trim(rwrt_handle h)
     CU(cudaDeviceSynchronize());
     h->records.release();
     h->packed.release();
+    h->direct.release();
     h->rows_done.release();
     h->inv.release();
     h->state.release();
@@ -951,10 +1022,10 @@ int rwrt_last_run_stats(rwrt_handle h, double *stats3)
     return RWRT_OK;
 }
 
-int rwrt_last_host_stats(rwrt_handle h, double *stats4)
+int rwrt_last_host_stats(rwrt_handle h, double *stats5)
 {
-    if (!h || !stats4) return fail(RWRT_ERR_ARG, "rwrt_last_host_stats: NULL argument");
-    for (int i = 0; i < 4; ++i) stats4[i] = h->host_stats[i];
+    if (!h || !stats5) return fail(RWRT_ERR_ARG, "rwrt_last_host_stats: NULL argument");
+    for (int i = 0; i < 5; ++i) stats5[i] = h->host_stats[i];
     return RWRT_OK;
 }
 
@@ -1044,6 +1115,18 @@ int rwrt_ray_run_rk4(rwrt_handle h, int nsource, const int32_t *src_member, int 
     return RWRT_OK;
 }
 
+// how the windows of a host-buffer call travel (see hx_on_window): RWRT_HOST_ROUTE = auto (default) | hx | direct | alt
+static void hx_configure(HostExpand *hx)
+{
+    cudaPointerAttributes at;
+    hx->can_direct = cudaPointerGetAttributes(&at, hx->out7_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    hx->route_mode = 0;
+    if (const char *e = getenv("RWRT_HOST_ROUTE"))
+        hx->route_mode = !strcmp(e, "hx") ? 1 : !strcmp(e, "direct") ? 2 : !strcmp(e, "alt") ? 3 : 0;
+    if (hx->route_mode == 1) hx->can_direct = false;
+}
+
 static int host_windows_default(size_t nout_doubles) { return (int)((nout_doubles * sizeof(double)) >> 29); }
 
 int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
@@ -1052,6 +1135,7 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
                           double *out7_host, void *stream)
 {
     if (!h || !out7_host) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45_d2h: NULL argument");
+    for (double &x : h->host_stats) x = 0;
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaSetDevice(h->device));
     const long long N = 3LL * nsource * nzwn;
@@ -1075,6 +1159,7 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
         hx.nt = nt;
         hx.copy_stream = copy_stream;
         hx.row0_only = false;
+        hx_configure(&hx);
         rc = run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7,
                       accepted, attempts, status, total_accepted, stream, nwin, nullptr, nullptr, &hx);
         if (rc == RWRT_OK) {
@@ -1148,6 +1233,7 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
                        (double)nsource * (src_member ? 20 : 16) + (double)nzwn * 8;
     h->host_stats[2] = nwin;
     h->host_stats[3] = 0;
+    h->host_stats[4] = 0;
     HostCopyCtx ctx;
     ctx.copy_stream = nullptr;
     ctx.ev[0] = ctx.ev[1] = nullptr;
@@ -1172,6 +1258,7 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
     } while (0)
     CUX(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
     hx.copy_stream = ctx.copy_stream;
+    hx_configure(&hx);
     CUX(cudaEventCreateWithFlags(&ctx.ev[0], cudaEventDisableTiming));
     CUX(cudaEventCreateWithFlags(&ctx.ev[1], cudaEventDisableTiming));
     CUX(cudaMemcpyAsync(arena + o_u, u, ng * 4, cudaMemcpyHostToDevice, s));

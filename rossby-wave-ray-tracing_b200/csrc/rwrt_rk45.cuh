@@ -173,13 +173,9 @@ __global__ void __launch_bounds__(256) fill_static_slots(RunParams p)
 #endif
 constexpr int EX_SLOTS = RWRT_EX_SLOTS, EX_ROWS = RWRT_EX_ROWS, EX_STRIDE = EX_ROWS * 8 + 1;   // doubles per slot in the tile (odd: no conflicts)
 static_assert(EX_SLOTS % 32 == 0 && EX_ROWS % 8 == 0 && EX_SLOTS * EX_STRIDE * 8 <= 48 * 1024, "expand_records tile");
-#ifndef RWRT_EXPAND_PIPELINED
-#define RWRT_EXPAND_PIPELINED 1
-#endif
 #ifndef RWRT_EX_TILES
 #define RWRT_EX_TILES 6
 #endif
-#if RWRT_EXPAND_PIPELINED
 // A block walks EX_TILES row tiles of its 32 slots: the records of tile i + 1 are requested (into registers) before
 // tile i is written out, so reads and writes overlap inside a block and the slot -> ray -> rows_done lookups are paid
 // once per block instead of once per tile (the one-tile-per-block form ran at 4.7 TB/s, latency-bound on that
@@ -195,7 +191,8 @@ __global__ void __launch_bounds__(256, RWRT_EX_MINBLOCKS) expand_records(RunPara
     const long long slot0 = (long long)blockIdx.x * EX_SLOTS;
     const int block_row0 = p.it_begin + blockIdx.y * EX_ROWS_PER_BLOCK;
     const int block_row1 = min(p.it_end, block_row0 + EX_ROWS_PER_BLOCK);
-    const size_t pl = (size_t)p.nt * p.N;
+    const size_t pl = p.out_pl;                                             // planes of the t = 0 row (constants of no-root slots)
+    const size_t dpl = p.dst_pl;                                            // planes of the destination rows
     const double n = qnan();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = lane >> 2, c = lane & 3;                                // row within a pass of 8, 16-byte piece of the record
@@ -268,77 +265,13 @@ __global__ void __launch_bounds__(256, RWRT_EX_MINBLOCKS) expand_records(RunPara
                 for (int half = 0; half < EX_SLOTS / 32; ++half) {
                     const long long slot = slot0 + 32 * half + lane;
                     if (slot < p.N)
-                        __stcs(p.out + (size_t)plane * pl + (size_t)it * p.N + slot, tile[(32 * half + lane) * EX_STRIDE + r * 8 + plane]);
+                        __stcs(p.dst + (size_t)plane * dpl + (size_t)(it - p.dst_it0) * p.N + slot, tile[(32 * half + lane) * EX_STRIDE + r * 8 + plane]);
                 }
             }
         }
         __syncthreads();                                                   // the tile is free again
     }
 }
-#else
-constexpr int EX_ROWS_PER_BLOCK = EX_ROWS;
-__global__ void __launch_bounds__(256) expand_records(RunParams p)
-{
-    __shared__ double tile[EX_SLOTS * EX_STRIDE];
-    const long long slot0 = (long long)blockIdx.x * EX_SLOTS;
-    const int row0 = p.it_begin + blockIdx.y * EX_ROWS;
-    const size_t pl = (size_t)p.nt * p.N;
-    const double n = qnan();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rr = lane >> 2, c = lane & 3;                                // row within a pass of 8, 16-byte piece of the record
-    // load phase: warp w fills slots w, w + 8, ... of the tile
-#pragma unroll
-    for (int q = 0; q < EX_SLOTS / 8; ++q) {
-        const int s = warp + 8 * q;
-        const long long slot = slot0 + s;
-        if (slot >= p.N) break;
-        const int li = p.inv[slot];
-        double *t = tile + s * EX_STRIDE;
-        if (li < 0) {   // NaN-root slot: planes 0..4 keep their t = 0 value, ug / vg are NaN
-            double a = (2 * c < 5) ? p.out[(size_t)(2 * c) * pl + slot] : n;
-            double b = (2 * c + 1 < 5) ? p.out[(size_t)(2 * c + 1) * pl + slot] : n;
-#pragma unroll
-            for (int h = 0; h < EX_ROWS / 8; ++h) {
-                t[(rr + 8 * h) * 8 + 2 * c] = a;
-                t[(rr + 8 * h) * 8 + 2 * c + 1] = b;
-            }
-            if (blockIdx.y == 0 && p.it_begin == 1 && lane == 0) {
-                if (p.accepted) p.accepted[slot] = 0;
-                if (p.attempts) p.attempts[slot] = 0;
-                if (p.status) p.status[slot] = 0;
-            }
-        } else {
-            const int rd = p.rows_done[li];
-            const double2 *rec = reinterpret_cast<const double2 *>(p.rec + ((size_t)li * p.rec_rows) * 8);
-#pragma unroll
-            for (int h = 0; h < EX_ROWS / 8; ++h) {
-                const int it = row0 + rr + 8 * h;
-                double2 v = make_double2(n, n);
-                if (it < rd && it < p.it_end) v = __ldcs(rec + (size_t)(it - p.it_begin) * 4 + c);
-                t[(rr + 8 * h) * 8 + 2 * c] = v.x;
-                t[(rr + 8 * h) * 8 + 2 * c + 1] = v.y;
-            }
-        }
-    }
-    __syncthreads();
-    // store phase: warp w writes rows w, w + 8, ... of all seven planes; per (plane, row) EX_SLOTS consecutive
-    // slots = 512 contiguous bytes, in back-to-back 256-byte stores
-#pragma unroll
-    for (int j = 0; j < EX_ROWS / 8; ++j) {
-        const int r = warp + 8 * j, it = row0 + r;
-        if (it >= p.it_end) break;
-#pragma unroll
-        for (int plane = 0; plane < 7; ++plane) {
-#pragma unroll
-            for (int half = 0; half < EX_SLOTS / 32; ++half) {
-                const long long slot = slot0 + 32 * half + lane;
-                if (slot < p.N)
-                    __stcs(p.out + (size_t)plane * pl + (size_t)it * p.N + slot, tile[(32 * half + lane) * EX_STRIDE + r * 8 + plane]);
-            }
-        }
-    }
-}
-#endif
 
 // Per-lane ray state kept in registers; the seven stage vectors K1..K7 live in shared memory
 // (ks[stage][component][thread], conflict-free), which keeps the kernel at <= 128 registers and

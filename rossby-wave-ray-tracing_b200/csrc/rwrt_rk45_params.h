@@ -14,6 +14,9 @@ struct RunParams {
     double tstep, ttotal, rtol, atol, gmin, cut;
     double *out;                // 7 planes, each (nt, N)
     size_t out_pl;              // doubles between the planes of `out` (nt * N; N when only row 0 exists: host-side expansion)
+    double *dst;                // expand_records writes row `it` of plane c to dst[c * dst_pl + (it - dst_it0) * N + slot]:
+    size_t dst_pl;              // normally `out` itself (dst_pl = nt * N, dst_it0 = 0); a window-sized buffer when the rows
+    int dst_it0;                // of one time window are expanded for a direct copy to the host (rwrt_real2d_host)
     const int32_t *live;        // compacted list of live slots
     long long nlive;
     double *state;              // (nlive, RWRT_STATE): y[5], f[5], h_abs, cos(prev lat), t, prev lon, prev lat, counters

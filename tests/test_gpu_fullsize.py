@@ -172,10 +172,11 @@ def test_schedule_and_gather_independence(monkeypatch):
 
 
 def test_host_entry_quarter_size(monkeypatch):
-    """rwrt_real2d_host at a quarter of C2 (287 k slots, 5.8 GB of result planes in pageable host memory): the default
-    form (ray records cross the link window by window into pinned staging buffers, host threads write the planes --
-    every staging buffer and both device window buffers are reused several times) and the device-expanded form
-    (RWRT_HOST_EXPAND=0) must both return the bits of the device-resident run, twice in a row on one handle."""
+    """rwrt_real2d_host at a quarter of C2 (287 k slots, 5.8 GB of result planes in pinned host memory): the default
+    form (packed rows of the live rays cross the link window by window into pinned staging buffers, host threads write
+    the planes, windows go straight into the caller's planes when the threads are behind -- every staging buffer and
+    all device window buffers are reused several times), every forced routing, and the device-expanded form
+    (RWRT_HOST_EXPAND=0) must return the bits of the device-resident run, repeatedly on one handle."""
     nlon, nlat = 360, 181
     slon_deg, slat_deg = synthetic.all_gridpoint_sources(nlon, nlat, 88.0)
     slon_deg, slat_deg = slon_deg[1::4], slat_deg[1::4]
@@ -192,8 +193,12 @@ def test_host_entry_quarter_size(monkeypatch):
         lon, lat = synthetic.grid_coords(nlon, nlat)
         cl, sn = np.cos(lat), np.sin(lat)
         slon, slat = np.radians(slon_deg), np.radians(slat_deg)
-        host = np.empty((7, nt, N))
-        for env in ({}, {"RWRT_HOST_THREADS": "3", "RWRT_HOST_WINDOWS": "11"}, {"RWRT_HOST_EXPAND": "0"}, {}):
+        import torch
+        host_t = torch.empty((7, nt, N), dtype=torch.float64, pin_memory=True)   # pinned: windows may also go direct
+        host = host_t.numpy()
+        for env in ({}, {"RWRT_HOST_THREADS": "3", "RWRT_HOST_WINDOWS": "11"}, {"RWRT_HOST_EXPAND": "0"}, {"RWRT_HOST_ROUTE": "hx"},
+                    {"RWRT_HOST_ROUTE": "alt"}, {"RWRT_HOST_ROUTE": "direct", "RWRT_HOST_WINDOWS": "5"},
+                    {"RWRT_HOST_THREADS": "1"}, {}):     # one writer thread: the backlog rule sends windows direct
             for k, val in env.items():
                 monkeypatch.setenv(k, val)
             try:

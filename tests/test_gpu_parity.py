@@ -227,12 +227,20 @@ def test_c_abi_host_entry_equals_facade(monkeypatch):
     L = lib.load()
     nt = w.nt
     cl, sn = np.cos(lat), np.sin(lat)
-    for chunk_mb, expand in (("1", "1"), ("4", "1"), ("9", "1"), ("30", "1"), ("1", "0"), ("4", "0")):
+    import torch
+    pinned_t = torch.empty((7, nt, 3, ns, 3), dtype=torch.float64, pin_memory=True)
+    # windows, RWRT_HOST_EXPAND (1: packed rows travel, host threads expand; 0: the device expands), RWRT_HOST_ROUTE
+    # (which windows are copied straight into PINNED caller planes instead: none / all / every other / by backlog)
+    for chunk_mb, expand, route in (("1", "1", "hx"), ("4", "1", "hx"), ("9", "1", "hx"), ("30", "1", "hx"), ("1", "0", "hx"),
+                                    ("4", "0", "hx"), ("9", "1", "direct"), ("30", "1", "alt"), ("9", "1", "alt"), ("30", "1", "auto"),
+                                    ("2", "1", "alt")):
         monkeypatch.setenv("RWRT_HOST_WINDOWS", chunk_mb)
-        monkeypatch.setenv("RWRT_HOST_EXPAND", expand)   # 1: records travel, host threads expand; 0: device expands
+        monkeypatch.setenv("RWRT_HOST_EXPAND", expand)
+        monkeypatch.setenv("RWRT_HOST_ROUTE", route)
         h = lib.vp()
         lib.check(L.rwrt_create(0, 144, 73, 1, 1, C.byref(h)))
-        out = np.full((7, nt, 3, ns, 3), -7.0)
+        out = np.full((7, nt, 3, ns, 3), -7.0) if route == "hx" else pinned_t.numpy()   # pageable memory never goes direct
+        out.fill(-7.0)
         acc = np.full(3 * ns * 3, -1, dtype=np.int64)
         status = np.full(3 * ns * 3, -1, dtype=np.int8)
         total = np.zeros(1, dtype=np.int64)
@@ -241,10 +249,27 @@ def test_c_abi_host_entry_equals_facade(monkeypatch):
                                      days * 86400.0, 1e-6, 1e-6, 1e-3, 0.1, lib.MODE_FAST, lib.ptr(out), lib.ptr(acc),
                                      lib.ptr(status), lib.ptr(total), None), "rwrt_real2d_host")
         for k, n in enumerate(parity.NAMES):
-            assert np.array_equal(out[k], getattr(w, n), equal_nan=True), (chunk_mb, expand, n)
+            assert np.array_equal(out[k], getattr(w, n), equal_nan=True), (chunk_mb, expand, route, n)
         assert np.array_equal(acc.reshape(3, ns, 3), w.accepted) and int(total[0]) == w.total_accepted
         assert np.array_equal(status.reshape(3, ns, 3), w.status)
+        hs = (C.c_double * 5)()
+        lib.check(L.rwrt_last_host_stats(h, hs))
+        if expand == "1" and route == "direct":
+            assert hs[4] == hs[2] > 0           # every window went straight into the pinned planes
+        if expand == "1" and route == "alt" and hs[2] >= 2:
+            assert 0 < hs[4] < hs[2]
+        if route == "hx":
+            assert hs[4] == 0
         L.rwrt_destroy(h)
+    # the facade's delivery (rwrt_ray_run_rk45_d2h: full planes on the device) with pinned result planes and mixed routes
+    for route in ("alt", "direct"):
+        monkeypatch.setenv("RWRT_HOST_ROUTE", route)
+        monkeypatch.setenv("RWRT_HOST_WINDOWS", "7")
+        w2 = make_wr(u, v, zwn, slon, slat, days)
+        w2.pin_results = True
+        w2.ray_run(mode="numpy", inte_method="rk45")
+        assert np.array_equal(w2._host_planes(), w._host_planes(), equal_nan=True), route
+        assert np.array_equal(w2.d_out.cpu().numpy(), w._host_planes(), equal_nan=True), route
 
 
 def test_empty_and_error_paths():

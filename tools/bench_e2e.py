@@ -54,10 +54,10 @@ def main():
             t0 = time.perf_counter()
             call()
             ts.append(1e3 * (time.perf_counter() - t0))
-        hs = (C.c_double * 4)()
+        hs = (C.c_double * 5)()
         L.rwrt_last_host_stats(h, hs)
         print(f"{setting or 'default':50s} ms/pass min {min(ts):7.1f} median {sorted(ts)[len(ts)//2]:7.1f}   "
-              f"d2h {hs[0]/1e9:.2f} GB, {int(hs[2])} windows, {int(hs[3])} threads, steps {int(tot_h.item())}", flush=True)
+              f"d2h {hs[0]/1e9:.2f} GB, {int(hs[2])} windows ({int(hs[4])} direct), {int(hs[3])} threads, steps {int(tot_h.item())}", flush=True)
         for k in env:
             del os.environ[k]
     L.rwrt_destroy(h)
