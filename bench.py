@@ -399,6 +399,16 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    # diagnostics only: PCIe generation / performance state / SM clock while the host-buffer calls run (the GPU is ~15 %
+    # busy in them; per-call times drift on some boxes and this shows whether the link or the clocks moved with them)
+    link_rows, link_proc = [], None
+    try:
+        link_proc = subprocess.Popen(["nvidia-smi", "--query-gpu=pcie.link.gen.current,pcie.link.width.current,pstate,clocks.sm",
+                                      "--format=csv,noheader,nounits", "-lms", "100", "-i", str(dev.index or 0)],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        threading.Thread(target=lambda: [link_rows.append(ln.strip()) for ln in link_proc.stdout], daemon=True).start()
+    except Exception:
+        link_proc = None
     reps = max(1, min(a.steps, 8))
     t0 = time.perf_counter()
     steps = 0
@@ -415,6 +425,18 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    link = None
+    try:
+        if link_proc is not None:
+            link_proc.terminate()
+            link_proc.wait(timeout=2)
+            cols = [[c.strip() for c in r.split(",")] for r in link_rows if r.count(",") == 3]
+            if cols:
+                link = {"pcie_gen": sorted({c[0] for c in cols}), "pcie_width": sorted({c[1] for c in cols}),
+                        "pstate": sorted({c[2] for c in cols}), "sm_mhz": [min(float(c[3]) for c in cols), max(float(c[3]) for c in cols)],
+                        "samples": len(cols)}
+    except Exception:
+        link = None
     import ctypes as C
     hs = (C.c_double * 5)()
     lib.check(L.rwrt_last_host_stats(h, hs), "rwrt_last_host_stats")   # bytes the library actually moved in the last call
@@ -426,6 +448,7 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
     return {"value": float(s.item()) / float(t.item()), "unit": "steps/s", "h2d_bytes_per_step": int(hs[1]),
             "d2h_bytes_per_step": int(hs[0]), "result_bytes_per_step": d2h, "ms_per_step": 1e3 * float(t.item()) / reps,
             "ms_per_call": per_rep,          # this rank's calls (the value is total steps / total time, max over ranks)
+            "link_during_calls": link,
             "api": "rwrt_real2d_host (C ABI, host pointers; pinned inputs and result arrays)", "transfer": how}
 
 
