@@ -493,8 +493,9 @@ int rwrt_ray_init(rwrt_handle h, int nsource, const double *src_lon, const doubl
 // follow-up work (the host entry copies the finished rows to the host on another stream).
 typedef int (*window_hook)(void *ctx, int it_begin, int it_end, cudaStream_t s);
 
-// Host-side expansion (rwrt_real2d_host): the ray records of every time window travel to the host instead of the
-// reference-layout rows (13 GB instead of 23 GB on C2) and host threads write the caller's arrays from them.
+// Host-side expansion (rwrt_real2d_host, rwrt_ray_run_rk45_d2h): the rows of every time window travel to the host as
+// packed planes of the live rays instead of reference-layout rows (11.6 GB instead of 23.2 GB on C2) and host threads
+// write the caller's arrays from them (details above hx_worker and hx_on_window).
 constexpr int HX_STAGES = 4;
 struct HostExpand {
     // set by the caller
@@ -1327,9 +1328,9 @@ int rwrt_real2d_host(rwrt_handle h, const float *u, const float *v, const double
     if (!h || !u || !v || !lon || !lat || !src_lon || !src_lat || !zwn || !out7_host)
         return fail(RWRT_ERR_ARG, "rwrt_real2d_host: NULL argument");
     if (nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_real2d_host: bad sizes");
-    // Default: the ray records travel and host threads write the caller's arrays from them (RWRT_HOST_EXPAND=0: the
-    // device expands and the reference-layout rows travel).  Runs without live rays / on the per-lane kernel have no
-    // records: they take the second form.
+    // Default: packed rows of the live rays travel and host threads write the caller's arrays from them
+    // (RWRT_HOST_EXPAND=0: the device expands and the reference-layout rows travel).  Runs without live rays / on the
+    // per-lane kernel have no ray records: they take the second form.
     bool use_hx = nt >= 2 && (long long)nsource * nzwn > 0;
     if (const char *e = getenv("RWRT_HOST_EXPAND")) use_hx = use_hx && atoi(e) != 0;
     if (use_hx) {
