@@ -53,7 +53,7 @@ def test_product_does_not_import_oracle():
     bad = re.compile(r"(^\s*(from|import)\s+oracle\b)|(#include\s+\"[^\"]*oracle)|(librwrt_oracle)|(rwrt_oracle\.c)", re.M)
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not bad.search(txt), f"{f} reaches into oracle/"
 
