@@ -462,7 +462,7 @@ def main():
     p.add_argument("--strict", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
-    p.add_argument("--cpu-sources", type=int, default=2000)
+    p.add_argument("--cpu-sources", type=int, default=4000)   # ~14 s of single-thread CPU work on the GPU box
     p.add_argument("--ref-sources", type=int, default=0)
     a = p.parse_args()
     if a.impl == "reference":
