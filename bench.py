@@ -33,6 +33,10 @@ sys.path.insert(0, ROOT)
 FLOP_PER_STEP = 1342.0          # 6 RHS x 167 + 340 step algebra (algorithmic fp64 flop)
 BYTES_PER_OUTPUT = 56.0         # 7 doubles written per (ray, output time)
 NOMINAL_FP64_TFLOPS = 37.2      # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+# context for every CPU figure in the line (the UNMODIFIED Python reference, measured in the build container)
+PY_REFERENCE_NOTE = ("For scale, BASELINE.md: the unmodified Python reference runs 1.6e4-1.9e4 accepted steps/s on one core "
+                     "(one batch) and 1.31e5 steps/s on 8 cores (8 processes x 200 sources) -- the C port timed here is "
+                     "about 60x faster per core, so ratios against it are conservative.")
 
 
 def workload(name, rank=0):
@@ -53,14 +57,15 @@ def workload(name, rank=0):
         slon, slat = synthetic.all_gridpoint_sources(nlon, nlat, 88.0)
         slon, slat = slon[rank % stride::stride], slat[rank % stride::stride]
         zwn, days = np.arange(1.0, 7.0), 30.0
-    elif name in ("c5", "c5-small"):
+    elif name in ("c5", "c5-small", "c5-full"):
         # BASELINE configs[4]: 0.25 deg Clim background, 1440 x 386 sources (|lat| <= 48.125 deg) x k=1..6 x 3 roots
-        # = 10.0 M ray slots, 60 days.  One GPU integrates one eighth of the sources (every 8th, offset by rank):
-        # 1.25 M slots, 50 GB of trajectories -- the per-GPU share of the 8-GPU run.
+        # = 10.0 M ray slots, 60 days.  c5-full: all of them (the `strong` block shards this list over the ranks);
+        # c5: one eighth (every 8th source, offset by rank): 1.25 M slots, 50 GB of trajectories -- the per-GPU share
+        # of an 8-GPU run as a weak-scaling workload (--workload c5); c5-small: 1/128 (quick checks).
         nlon, nlat = 1440, 721
         u, v = synthetic.clim(nlon, nlat)
         slon, slat = synthetic.all_gridpoint_sources(nlon, nlat, 48.125)
-        stride = 8 if name == "c5" else 128
+        stride = {"c5": 8, "c5-small": 128, "c5-full": 1}[name]
         slon, slat = slon[rank % stride::stride], slat[rank % stride::stride]
         zwn, days = np.arange(1.0, 7.0), 60.0
     elif name in ("c4", "c4-full"):
@@ -197,11 +202,11 @@ def run_reference_arm(a):
     value = steps / secs
     sample = (f"seeded random sample of {n} of the {a.workload} sources per step, split over {cores} processes "
               f"(oracle C restatement of the reference algorithm, gcc -O2 -ffp-contract=off; the Python reference "
-              f"itself cannot travel to this box: see DESIGN.md)")
+              f"itself cannot travel to this box: see DESIGN.md).  " + PY_REFERENCE_NOTE)
     line = {"impl": "reference", "metric": "accepted RK45 ray-steps/s (fp64)", "value": value, "unit": "steps/s",
             "n_gpus": 0, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": a.workload, "sample_sources_per_step": n},
+            "config": {"workload": a.workload, "sample_sources_per_step": n, "cores": cores},
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -267,6 +272,7 @@ def run_ours(a):
                                       lib.ptr(out), lib.ptr(acc), None, None, lib.ptr(total), sp), "rwrt_ray_run_rk45")
 
     stats = (C.c_double * 3)()
+    times = (C.c_double * 4)()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -278,16 +284,18 @@ def run_ours(a):
         dist.barrier()
     sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    kern_ms, steps_done, launches = [], 0, 0
+    kern_ms, integ_ms, steps_done, launches = [], [], 0, 0
     torch.cuda.synchronize()
     for i in range(a.steps):
         ev[i][0].record(stream)
         one_step()
         ev[i][1].record(stream)
         flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
-        L.rwrt_last_run_stats(h, stats)     # syncs on the integrate kernels' end event
+        L.rwrt_last_run_stats(h, stats)     # syncs on the run's end event
+        L.rwrt_last_run_times(h, times)     # CUDA events recorded by the library on the launching stream, around the kernels
         launches += int(stats[0]) + 1       # + ray_init
         kern_ms.append(stats[2])
+        integ_ms.append(times[1])           # the integrate kernel alone (the dominant kernel)
         steps_done += int(total.item())
     torch.cuda.synchronize()
     if world > 1:
@@ -309,14 +317,36 @@ def run_ours(a):
     if not a.no_e2e:
         e2e = run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags, world, dev)
 
+    # ---- the same pass with the ray records as the native result (no transpose to the reference planes) ----
+    records = None
+    if not a.no_records and "member_of" not in wl:
+        records = run_records(a, L, h, d, nsource, nzwn, nt, N, tstep, ttotal, flags, sp, stream, flush, dev)
+    # ---- grid-only delivery end to end (host inputs -> sweep -> all-reduce -> grids on the host) ----
+    e2e_grid = None
+    if not a.no_e2e and "member_of" not in wl:
+        e2e_grid = run_e2e_grid(a, wl, nsource, world, rank, dev)
+    del out
+    torch.cuda.empty_cache()
+    L.rwrt_trim(h)
+    # ---- north_star's multi-GPU path: the 10 M-slot 0.25-degree sweep sharded over the ranks, gridded, all-reduced ----
+    strong = None
+    if not a.no_strong and (a.workload == "c2" or a.strong):   # part of the default (driver) line; opt-in for other workloads
+        strong = run_strong(a, L, rank, world, local, dev, flags)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (rk45_integrate; prepare + fill are inside the same event pair) ----
+    # ---- roofline of the dominant kernel: rk45_integrate_coop alone, timed by CUDA events on its stream ----
     peak_tf = C.c_double(0)
     L.rwrt_measure_fp64_peak(h, C.byref(peak_tf))
-    kms = float(np.mean(kern_ms))
+    if a.save_peak:
+        with open(a.save_peak, "w") as f:
+            f.write(f"rwrt_measure_fp64_peak (register-resident DFMA chains, 8 per thread, 8 x 256 threads per SM, best of 5): "
+                    f"{peak_tf.value:.3f} TFLOP/s; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = {NOMINAL_FP64_TFLOPS} TFLOP/s; "
+                    f"clocks during the timed region of this run: {json.dumps(clocks)}\n")
+    step_ms = float(np.mean(kern_ms))
+    kms = float(np.mean(integ_ms)) if integ_ms and min(integ_ms) > 0 else step_ms
     steps_per_launch = steps_done / a.steps
     achieved_tf = steps_per_launch * FLOP_PER_STEP / (kms * 1e-3) / 1e12
     peaks = {}
@@ -326,18 +356,28 @@ def run_ours(a):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_alg = steps_per_launch / 1.07 * BYTES_PER_OUTPUT   # ~1.07 accepted steps per (ray, output time)
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the integrate kernel from the committed ncu capture
+    traffic = traffic_step = traffic_src = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the COMMITTED ncu --set full captures (not measured in this run)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if tj.get("workload") == a.workload:
             traffic = tj.get("dram_bytes_per_launch")
+            traffic_step = tj.get("dram_bytes_per_step")
+            traffic_src = tj.get("source")
     except Exception:
         pass
-    roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf.value or NOMINAL_FP64_TFLOPS,
-            "unit": "TFLOP/s", "frac": achieved_tf / (peak_tf.value or NOMINAL_FP64_TFLOPS),
-            "peak_source": "measured DFMA-chain microbenchmark in this run (rwrt_measure_fp64_peak); nominal 37.2",
+    peak = peak_tf.value or NOMINAL_FP64_TFLOPS
+    roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved_tf / peak,
+            "peak_source": "measured DFMA-chain microbenchmark in this run (rwrt_measure_fp64_peak); nominal 37.2; "
+                           "MEASURED_PEAKS.json has no FP64 figure",
             "flop_per_step": FLOP_PER_STEP, "kernel_ms": kms, "traffic": traffic,
-            "kernel": "rk45_integrate_coop (+ rk45_prepare and the expand_records transpose inside the same event pair)",
+            "traffic_source": traffic_src and f"committed capture, not measured in this run: {traffic_src}",
+            "traffic_step": traffic_step,
+            "kernel": "rk45_integrate_coop<OUT_ROWS> alone (CUDA events on the launching stream around its launch, "
+                      "rwrt_last_run_times[1])",
+            "step": {"ms": step_ms, "frac": steps_per_launch * FLOP_PER_STEP / (step_ms * 1e-3) / 1e12 / peak,
+                     "what": "the whole pass in one event pair: compaction result wait excluded, rk45_prepare + integrator + "
+                             "expand_records transpose to the reference planes"},
             "hbm": {"achieved": hbm_alg / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_alg / (kms * 1e-3) / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
@@ -349,7 +389,7 @@ def run_ours(a):
         st, slowest, wall, n = cpu_sample(a.workload, a.cpu_sources, 1, seed=0)
         cpu = {"value": st / slowest, "unit": "steps/s", "cores": 1, "kind": "port",
                "sample": f"seeded random sample of {n} sources of the workload ({st} accepted steps, {slowest:.1f} s), "
-                         "oracle C restatement, single thread"}
+                         "oracle C restatement, single thread.  " + PY_REFERENCE_NOTE}
     line = {"metric": "accepted RK45 ray-steps/s (fp64)", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -358,11 +398,193 @@ def run_ours(a):
                        "mode": "strict" if a.strict else "fast", "accepted_steps_per_step_per_gpu": steps_per_launch,
                        "l2": f"flushed between timed iterations (256 MB write); outputs ({7 * nt * N * 8 / 1e9:.1f} GB) exceed L2 anyway",
                        "timed_region": "rwrt_ray_init + rwrt_ray_run_rk45 (fields resident in HBM)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+            "clocks": clocks, "e2e": e2e, "e2e_grid": e2e_grid, "gpu_launches": launches, "roofline": roof,
+            "records": records, "strong": strong, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     L.rwrt_destroy(h)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_records(a, L, h, d, nsource, nzwn, nt, N, tstep, ttotal, flags, sp, stream, flush, dev):
+    """The timed pass of `value` with the ray records as the native result (rwrt_ray_run_rk45_records): the integrator's
+    64-byte records stay on the device and the transpose to the reference's seven planes happens only on demand."""
+    import torch
+    from rwrt_b200 import lib
+    row0 = torch.empty((7, N), dtype=torch.float64, device=dev)
+    acc = torch.zeros(N, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    times = (C.c_double * 4)()
+
+    def one():
+        lib.check(L.rwrt_ray_init(h, nsource, lib.ptr(d["slon"]), lib.ptr(d["slat"]), None, nzwn, lib.ptr(d["zwn"]), 0.0, 1,
+                                  lib.ptr(row0), sp), "rwrt_ray_init")
+        lib.check(L.rwrt_ray_run_rk45_records(h, nsource, None, nzwn, nt, tstep, ttotal, 1e-6, 1e-6, 1e-3, 0.1, flags,
+                                              lib.ptr(row0), lib.ptr(acc), None, None, lib.ptr(total), sp),
+                  "rwrt_ray_run_rk45_records")
+    try:
+        one()
+        flush.zero_()
+        torch.cuda.synchronize()
+        ms, integ, steps = [], [], 0
+        for _ in range(a.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            one()
+            e1.record(stream)
+            flush.zero_()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+            L.rwrt_last_run_times(h, times)
+            integ.append(times[1])
+            steps += int(total.item())
+        return {"value": steps / (sum(ms) * 1e-3), "unit": "steps/s", "ms_per_step": float(np.mean(ms)),
+                "integrate_ms": float(np.mean(integ)),
+                "what": "rwrt_ray_init + rwrt_ray_run_rk45_records: same rays, results left as 64-byte ray records on the device "
+                        "(13 GB of DRAM writes per pass instead of 50.9 GB with the transpose); rwrt_records_expand / "
+                        "rwrt_grid_accumulate_records consume them on demand"}
+    except lib.RwrtError as e:
+        return {"value": None, "note": f"skipped: {e}"}
+
+
+def run_strong(a, L, rank, world, local, dev, flags):
+    """BASELINE configs[4] as ONE job: 0.25-degree Clim background, 1440 x 386 sources x k=1..6 x 3 roots = 10 005 120
+    ray slots, 60 days, the sources sharded over the ranks (dist.shard_indices); every rank runs rwrt_ray_sweep_grid on
+    its share (no trajectory arrays: the reference's layout would need 404 GB, wr.py:157-167) and the (3, 4320, 720)
+    int64 ray-density / flux accumulators are merged by ONE NCCL all-reduce -- both inside the event pair."""
+    import torch
+    import torch.distributed as dist
+    from rwrt_b200 import dist as rdist
+    from rwrt_b200 import gridding, lib
+    wl = workload("c5-full")
+    nlon, nlat = wl["nlon"], wl["nlat"]
+    nsrc_all, nzwn = len(wl["src_lon_deg"]), len(wl["zwn"])
+    idx = rdist.shard_indices(nsrc_all, rank, world, a.shard)
+    slon, slat = np.radians(wl["src_lon_deg"][idx]), np.radians(wl["src_lat_deg"][idx])
+    nsource = len(idx)
+    tstep, ttotal = 7200.0, wl["days"] * 86400.0
+    nt = int(ttotal / tstep) + 1
+    cell = (0.25, 0.25)
+    ncx, ncy = gridding.grid_shape(*cell)
+    h = lib.vp()
+    lib.check(L.rwrt_create(local, nlon, nlat, 1, 1, C.byref(h)), "rwrt_create")
+    stream = torch.cuda.current_stream()
+    sp = lib.vp(stream.cuda_stream)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
+         dict(u=wl["u"], v=wl["v"], lon=wl["lon"], lat=wl["lat"], cl=np.cos(wl["lat"]), sl=np.sin(wl["lat"]),
+              slon=slon, slat=slat, zwn=wl["zwn"]).items()}
+    lib.check(L.rwrt_bs_ready(h, lib.ptr(d["u"]), lib.ptr(d["v"]), lib.ptr(d["lon"]), lib.ptr(d["lat"]),
+                              lib.ptr(d["cl"]), lib.ptr(d["sl"]), None, None, sp), "rwrt_bs_ready")
+    grids = gridding.new_grids(*cell, dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    ar = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
+    def one_pass():
+        grids.zero_()
+        lib.check(L.rwrt_ray_sweep_grid(h, nsource, lib.ptr(d["slon"]), lib.ptr(d["slat"]), None, nzwn, lib.ptr(d["zwn"]), 0.0,
+                                        nt, tstep, ttotal, 1e-6, 1e-6, 1e-3, 0.1, flags, cell[0], cell[1], ncx, ncy,
+                                        lib.ptr(grids[0]), lib.ptr(grids[1]), lib.ptr(grids[2]), None, None, lib.ptr(total), sp),
+                  "rwrt_ray_sweep_grid")
+        ar[0].record(stream)
+        if world > 1:
+            dist.all_reduce(grids, op=dist.ReduceOp.SUM)      # the path's one collective (NCCL over NVLink)
+        ar[1].record(stream)
+
+    nsteps = max(1, min(a.steps, a.strong_steps))
+    one_pass()                                                # warm-up (also sizes the handle's work lists)
+    flush.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms, ms_ar, steps = [], [], 0
+    for _ in range(nsteps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        one_pass()
+        e1.record(stream)
+        flush.zero_()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+        ms_ar.append(ar[0].elapsed_time(ar[1]))
+        steps += int(total.item())
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    s = torch.tensor([float(steps)], dtype=torch.float64, device=dev)
+    per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
+    per_rank[rank] = sum(ms) / nsteps
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+    csum = gridding.checksum(grids)                           # of the all-reduced grids: must not depend on N
+    count_total = int(grids[0].sum().item())
+    L.rwrt_destroy(h)
+    return {"metric": "accepted RK45 ray-steps/s (fp64), whole 10 M-slot sweep incl. gridding + all-reduce",
+            "value": float(s.item()) / (float(t.item()) * 1e-3), "unit": "steps/s", "scaling": "strong", "n_gpus": world,
+            "steps": nsteps, "warmup": 1, "ms_per_step": float(t.item()) / nsteps,
+            "ms_allreduce": float(np.mean(ms_ar)), "allreduce_bytes": int(grids.numel() * 8),
+            "collective": "one torch.distributed all_reduce(SUM) of the (3, 4320, 720) int64 accumulators over NCCL" if world > 1
+                          else "none (1 rank)",
+            "per_rank_ms": [round(float(x), 2) for x in per_rank.tolist()], "shard": a.shard,
+            "accepted_steps_per_pass": float(s.item()) / nsteps, "grid_checksum": f"0x{csum:016x}",
+            "grid_samples": count_total,
+            "workload": f"c5-full: Clim 0.25deg background, {nsrc_all} sources x k=1..{nzwn} x 3 roots = {3 * nsrc_all * nzwn} ray slots "
+                        f"sharded over {world} GPU(s) ({3 * nsource * nzwn} on rank 0), 60 d, tstep 2 h, nt={nt}, gridded on 0.25deg cells "
+                        f"(three longitude circles); no (7, nt, N) arrays exist (they would be {7 * nt * 3 * nsrc_all * nzwn * 8 / 1e9:.0f} GB)",
+            "api": "rwrt_ray_sweep_grid (C ABI, device pointers) + torch.distributed.all_reduce"}
+
+
+def run_e2e_grid(a, wl, nsource, world, rank, dev):
+    """Grid-only delivery end to end through the package's public API (WR facade + gridding.sweep + dist.allreduce_grids):
+    every call uploads the winds and the sources from host memory, recomputes the basic state, sweeps, all-reduces the
+    grids and brings them to the host -- what a user who wants ray density / flux (not 23 GB of trajectories) runs."""
+    import torch
+    import torch.distributed as dist
+    from rwrt_b200 import dist as rdist
+    from rwrt_b200 import gridding
+    from rwrt_b200.wr import WR
+    nlon, nlat = wl["nlon"], wl["nlat"]
+    cell = (360.0 / nlon, 180.0 / (nlat - 1))
+    w = WR(len(wl["zwn"]), nsource, 7200.0, wl["days"] * 86400.0, 0.0, nx=nlon, ny=nlat, device=dev.index)
+    w.bs.lon, w.bs.lat = wl["lon"], wl["lat"]
+    w.set_zwn(wl["zwn"])
+    host = torch.empty((3,) + gridding.grid_shape(*cell), dtype=torch.int64, pin_memory=True)
+
+    def call():
+        w.bs.u, w.bs.v = wl["u"], wl["v"]                                  # host arrays: H2D inside bs.ready
+        w.bs.ready(xcyclic=True, keep_fields18=False, keep_diag=False)
+        w.set_source_array(wl["src_lon_deg"], wl["src_lat_deg"])           # degrees on the host, like the reference
+        g = gridding.sweep(w, *cell, want_accepted=False)
+        rdist.allreduce_grids(g)
+        host.copy_(g, non_blocking=True)
+        torch.cuda.synchronize()
+        return w.total_accepted
+
+    call()
+    if world > 1:
+        dist.barrier()
+    reps = max(1, min(a.steps, 8))
+    t0 = time.perf_counter()
+    steps, per = 0, []
+    for _ in range(reps):
+        t1 = time.perf_counter()
+        steps += call()
+        per.append(round(1e3 * (time.perf_counter() - t1), 1))
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    s = torch.tensor([float(steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    h2d = wl["u"].nbytes + wl["v"].nbytes + 4 * wl["lat"].nbytes + 2 * wl["lon"].nbytes + 16 * nsource + 8 * len(wl["zwn"])
+    w.clean()
+    return {"value": float(s.item()) / float(t.item()), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(host.numel() * 8 + 8), "ms_per_step": 1e3 * float(t.item()) / reps, "ms_per_call": per,
+            "api": "WR facade: bs.ready + gridding.sweep (rwrt_ray_sweep_grid) + dist.allreduce_grids + grids to pinned host memory",
+            "what": f"same sources and rays as `e2e`, delivered as (3, {host.shape[1]}, {host.shape[2]}) int64 ray-density / flux "
+                    "grids instead of seven trajectory arrays"}
 
 
 def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags, world, dev):
@@ -404,7 +626,7 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
     link_rows, link_proc = [], None
     try:
         link_proc = subprocess.Popen(["nvidia-smi", "--query-gpu=pcie.link.gen.current,pcie.link.width.current,pstate,clocks.sm",
-                                      "--format=csv,noheader,nounits", "-lms", "100", "-i", str(dev.index or 0)],
+                                      "--format=csv,noheader,nounits", "-lms", "1000", "-i", str(dev.index or 0)],
                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         threading.Thread(target=lambda: [link_rows.append(ln.strip()) for ln in link_proc.stdout], daemon=True).start()
     except Exception:
@@ -462,6 +684,12 @@ def main():
     p.add_argument("--strict", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-strong", action="store_true")
+    p.add_argument("--strong", action="store_true")
+    p.add_argument("--no-records", action="store_true")
+    p.add_argument("--strong-steps", type=int, default=3)
+    p.add_argument("--shard", default="stride", choices=["stride", "block"])
+    p.add_argument("--save-peak", default="")
     p.add_argument("--cpu-sources", type=int, default=4000)   # ~14 s of single-thread CPU work on the GPU box
     p.add_argument("--ref-sources", type=int, default=0)
     a = p.parse_args()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RWRT_ABI_VERSION 1
+#define RWRT_ABI_VERSION 2
 
 typedef struct rwrt_ctx *rwrt_handle;
 
@@ -47,6 +47,9 @@ typedef enum {
 /* flags for rwrt_ray_run_rk45 */
 #define RWRT_MODE_FAST 0u   /* FMA contraction allowed (default)                              */
 #define RWRT_MODE_STRICT 1u /* every operation a separate IEEE double op, reference order    */
+/* flag for rwrt_ray_sweep_grid: grid each time window's ray records with a second kernel instead of
+ * accumulating inside the integrator (same bits; kept as the cross-check of the fused form)       */
+#define RWRT_GRID_FROM_RECORDS 2u
 
 /* per-slot status codes written by rwrt_ray_run_rk45 (new, additive: the reference only has NaN) */
 #define RWRT_RAY_NO_ROOT 0   /* NaN root at t = 0: never propagates   */
@@ -156,6 +159,48 @@ int rwrt_grid_accumulate(rwrt_handle h, int64_t nslot, int nt, const double *out
                          int ncx, int ncy, int64_t *count, int64_t *fx, int64_t *fy, void *stream);
 
 /*
+ * Grid-only sweep: ray_initial + RK45 + gridding in one pass, with NO trajectory arrays.  What a global sweep
+ * (BASELINE configs[4]: 10^7 ray slots x 721 output times) must avoid is the reference's up-front result allocation
+ * of 7 * nt * N doubles (wr.py:157-167: 404 GB there); the quantities the gridding tool reads from the ray file
+ * (wr.py:947-959: rlon, rlat, rmwn, rug, rvg) are consumed where they are produced instead.  By default the
+ * integrator adds every output sample to count / fx / fy itself (three integer reductions per output row, same
+ * definition and same bits as rwrt_grid_accumulate on the trajectories of rwrt_ray_run_rk45); with
+ * RWRT_GRID_FROM_RECORDS the integration runs in time windows whose 64-byte ray records a second kernel grids.
+ * src_lon/src_lat (nsource) radians, zwn (nzwn): device pointers as in rwrt_ray_init.  count, fx, fy (ncx, ncy) int64
+ * are ACCUMULATED INTO (zero them first; one ncclAllReduce(sum) over them merges the ranks of a sharded sweep --
+ * integer sums, so the result does not depend on the sharding).  accepted (N) / status (N) / total_accepted: optional.
+ */
+int rwrt_ray_sweep_grid(rwrt_handle h, int nsource, const double *src_lon, const double *src_lat,
+                        const int32_t *src_member, int nzwn, const double *zwn, double freq, int nt, double tstep,
+                        double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
+                        double dlon_deg, double dlat_deg, int ncx, int ncy, int64_t *count, int64_t *fx, int64_t *fy,
+                        int64_t *accepted, int8_t *status, int64_t *total_accepted, void *stream);
+
+/*
+ * rwrt_ray_run_rk45 with the RAY RECORDS as the native result: the integrator's own output -- one 64-byte record
+ * (lon, lat, k, l, A, u_g, v_g, pad) per live ray and output row, rec[ray][row - 1][8] for rows 1..nt-1 -- stays in
+ * library memory and the transpose to the reference's seven planes (wr.py:160-167, 868-885) happens only on demand
+ * (rwrt_records_expand, any row range) or never (rwrt_grid_accumulate_records).  out7_row0: (7, N) = row 0 of the
+ * seven planes as rwrt_ray_init(..., nt = 1, ...) writes it (copied to the handle).  The records stay valid until the
+ * next run or rwrt_trim on this handle.  Fails with RWRT_ERR_NOMEM when nray * (nt - 1) * 64 B does not fit.
+ */
+int rwrt_ray_run_rk45_records(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
+                              double ttotal, double rtol, double atol, double min_step_factor, double cut_off,
+                              uint32_t flags, const double *out7_row0, int64_t *accepted, int64_t *attempts,
+                              int8_t *status, int64_t *total_accepted, void *stream);
+/* device pointers into the handle's records (any output pointer may be NULL): nray live rays; rec (nray, rec_rows, 8);
+ * rows_done[ray] = rows 1 .. rows_done-1 are valid (a ray that died at row r has rows_done = r: wr.py:838-855);
+ * ray_slot[ray] = its slot; slot_to_ray[slot] = its ray or -1 for a slot without a real root. */
+int rwrt_records_info(rwrt_handle h, int64_t *nray, int *rec_rows, const double **rec, const int32_t **rows_done,
+                      const int32_t **ray_slot, const int32_t **slot_to_ray);
+/* rows [row_begin, row_end) (1 <= row_begin) of the seven reference-layout planes from the records:
+ * dst7 (7, row_end - row_begin, N) device. */
+int rwrt_records_expand(rwrt_handle h, int row_begin, int row_end, double *dst7, void *stream);
+/* rwrt_grid_accumulate over the handle's records (all rows); count / fx / fy are accumulated into. */
+int rwrt_grid_accumulate_records(rwrt_handle h, double dlon_deg, double dlat_deg, int ncx, int ncy, int64_t *count,
+                                 int64_t *fx, int64_t *fy, void *stream);
+
+/*
  * Whole ray path with HOST buffers (the call main_wr.real2d_hnf makes, main_wr.py:66-89, minus
  * NetCDF): H2D of u, v, coordinates, sources; BS.ready; ray_initial; RK45; the seven result arrays
  * (wr.py:767-781) in out7_host.  Synchronises before returning.
@@ -194,6 +239,12 @@ int rwrt_trim(rwrt_handle h);
 /* counters of the last rwrt_ray_run_rk45 on this handle (host side, after a sync):
  * [0] kernels launched, [1] live rays, [2] ms of the integrate kernel(s) by CUDA events */
 int rwrt_last_run_stats(rwrt_handle h, double *stats3);
+
+/* CUDA-event times of the last run on this handle (ms, after a sync): [0] whole run (as stats3[2]), [1] the integrate
+ * kernel alone (sum over its time windows) -- the dominant kernel bench.py's roofline is quoted on --, [2] t = 0 work
+ * before the first window (rk45_prepare), [3] the rest (expand_records / pack_records / grid_records between and after
+ * the windows). */
+int rwrt_last_run_times(rwrt_handle h, double *ms4);
 
 /* the last rwrt_real2d_host on this handle: [0] bytes copied device -> host, [1] bytes host -> device, [2] time windows,
  * [3] host threads that wrote result planes (0: the device expanded all of them), [4] windows whose device-expanded rows

@@ -77,8 +77,13 @@ struct rwrt_ctx {
     int sm_count = 0;
     bool ready = false;
     double lon0 = 0, dlon = 0, lat0 = 0, dlat = 0;
-    DevBuf fpk, scratch, trig, live, state, counters, blockcnt, inv, rows_done, records, packed, direct;
+    DevBuf fpk, scratch, trig, live, state, counters, blockcnt, inv, rows_done, records, packed, direct, row0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    std::vector<cudaEvent_t> ev_win;   // per time window: start / end of the integrate kernel (timing of the dominant kernel alone)
+    int n_win_timed = 0;
+    RunParams last_p;                  // parameters of the last run that kept its ray records on the handle (rwrt_ray_run_rk45_records)
+    bool have_records = false;
+    bool last_strict = false;
     cudaStream_t aux = nullptr;  // side stream for work that is independent of the integrator
     bool timed = false;
     double last_launches = 0, last_nlive = 0;
@@ -329,23 +334,33 @@ int rwrt_create(int device, int nlon, int nlat, int xcyclic, int nmember, rwrt_h
     h->xcyclic = xcyclic ? 1 : 0;
     h->nmember = nmember;
     h->nlon_f = nlon + h->xcyclic;
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    h->sm_count = prop.multiProcessorCount;
+    {
+        int sms = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess) {
+            delete h;
+            return fail(RWRT_ERR_CUDA, "rwrt_create: %s", cudaGetErrorString(e));
+        }
+        h->sm_count = sms;
+    }
     size_t npk = (size_t)nmember * h->nlon_f * nlat * NPK * sizeof(double);
     if (h->fpk.reserve(npk) || h->trig.reserve(2 * (size_t)nlat * sizeof(double)) ||
         h->counters.reserve(8 * sizeof(unsigned long long))) {
         delete h;
         return fail(RWRT_ERR_NOMEM, "device allocation of the packed fields (%zu B) failed", npk);
     }
-    CU(cudaEventCreate(&h->ev0));
-    CU(cudaEventCreate(&h->ev1));
-    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     {
-        int lo = 0, hi = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = numerically largest = lowest priority
-        CU(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, lo));
+        int lo = 0, hi = 0;   // lo = numerically largest = lowest priority
+        cudaError_t e = cudaEventCreate(&h->ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, lo);
+        if (e != cudaSuccess) {
+            rwrt_destroy(h);   // releases whatever exists so far
+            return fail(RWRT_ERR_CUDA, "rwrt_create: %s", cudaGetErrorString(e));
+        }
     }
     *out = h;
     return RWRT_OK;
@@ -361,6 +376,9 @@ int rwrt_destroy(rwrt_handle h)
     h->records.release();
     h->packed.release();
     h->direct.release();
+    h->row0.release();
+    for (auto e : h->ev_win) cudaEventDestroy(e);
+    h->ev_win.clear();
     h->scratch.release();
     h->trig.release();
     h->live.release();
@@ -534,11 +552,48 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_
                     cudaStream_t s);
 #define RWRT_HX_UNSUPPORTED 12345   /* internal: the caller falls back to device-side expansion */
 
+// Gridding request of a run (rwrt_ray_sweep_grid): accumulators (ncx, ncy) int64 each, cells of (dlon, dlat) degrees.
+struct GridSpec {
+    double dlon = 0, dlat = 0;
+    int ncx = 0, ncy = 0;
+    long long *count = nullptr, *fx = nullptr, *fy = nullptr;
+    bool from_records = false;   // false: fused into the integrator (RED per output row); true: grid_records_kernel per window
+};
+// What a run keeps of its output rows
+enum { KEEP_PLANES = 0,          // the seven reference-layout planes in out7 (7, nt, N)         -- rwrt_ray_run_rk45
+       KEEP_RECORDS = 1,         // the per-ray records on the handle, out7 = row 0 only (7, N)  -- rwrt_ray_run_rk45_records
+       KEEP_NOTHING = 2 };       // nothing (the grids are the result), out7 = row 0 only         -- rwrt_ray_sweep_grid
+struct RunOpts {
+    int nwin = 1;
+    window_hook hook = nullptr;
+    void *hook_ctx = nullptr;
+    HostExpand *hx = nullptr;
+    const GridSpec *grid = nullptr;
+    int keep = KEEP_PLANES;
+};
+
+static cudaEvent_t *win_events(rwrt_handle h, int w)
+{
+    while ((int)h->ev_win.size() < 2 * (w + 1)) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        h->ev_win.push_back(e);
+    }
+    return h->ev_win.data() + 2 * w;
+}
+
 static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
                     double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
                     double *out7, int64_t *accepted, int64_t *attempts, int8_t *status, int64_t *total_accepted,
-                    void *stream, int nwin, window_hook hook, void *hook_ctx, HostExpand *hx = nullptr)
+                    void *stream, const RunOpts &opt)
 {
+    int nwin = opt.nwin;
+    window_hook hook = opt.hook;
+    void *hook_ctx = opt.hook_ctx;
+    HostExpand *hx = opt.hx;
+    const GridSpec *grid = opt.grid;
+    const bool row0_only = (hx && hx->row0_only) || opt.keep != KEEP_PLANES;
+    const bool fused_grid = grid && !grid->from_records;
     if (!h || nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45: bad sizes");
     if (!(tstep > 0)) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45: tstep must be positive");
     if (!h->ready) return fail(RWRT_ERR_STATE, "rwrt_ray_run_rk45 before rwrt_bs_ready");
@@ -548,6 +603,8 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     h->timed = false;
     h->last_launches = 0;
     h->last_nlive = 0;
+    h->n_win_timed = 0;
+    h->have_records = false;
     unsigned long long *ctr = (unsigned long long *)h->counters.p;  // [0] queue, [1] total accepted, [2] nlive
     CU(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), s));
     if (N == 0 || nt < 2) {
@@ -571,8 +628,10 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         // itself is 19 % faster (profiles/).  RWRT_RECORDS=0 writes the reference layout directly (v1-v13).
         const char *er = getenv("RWRT_RECORDS");
         use_records = !(er && atoi(er) == 0);
+        if (opt.keep == KEEP_RECORDS || (grid && grid->from_records)) use_records = true;
+        if (opt.keep == KEEP_NOTHING && fused_grid) use_records = false;   // no rows are stored at all
         if (use_records && h->inv.reserve((size_t)N * sizeof(int32_t))) return fail(RWRT_ERR_NOMEM, "slot map allocation failed");
-        launch_compact_live(N, (hx && hx->row0_only) ? (size_t)N : (size_t)nt * N, out7, slot_order ? (int)1 : nsource, slot_order ? (int)1 : nzwn, (int32_t *)h->live.p,
+        launch_compact_live(N, row0_only ? (size_t)N : (size_t)nt * N, out7, slot_order ? (int)1 : nsource, slot_order ? (int)1 : nzwn, (int32_t *)h->live.p,
                             use_records ? (int32_t *)h->inv.p : nullptr, ctr + 2, (int *)h->blockcnt.p, nblocks, s);
     }
     unsigned long long nlive = 0;
@@ -597,7 +656,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     p.gmin = fmin(min_step_factor * tstep, (tstep - 0) * 0.001);
     p.cut = cut_off * tstep / 3600.;
     p.out = out7;
-    p.out_pl = (hx && hx->row0_only) ? (size_t)N : (size_t)nt * N;
+    p.out_pl = row0_only ? (size_t)N : (size_t)nt * N;
     p.dst = out7;                                   // expand_records writes the planes themselves ...
     p.dst_pl = (size_t)nt * N;                      // (... except for a direct window of rwrt_real2d_host, see hx_on_window)
     p.dst_it0 = 0;
@@ -609,6 +668,19 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     p.status = (signed char *)status;
     p.queue = ctr;
     p.total_accepted = ctr + 1;
+    p.g_count = p.g_fx = p.g_fy = nullptr;
+    p.g_dlon = p.g_dlat = 1.0;
+    p.g_ncx = p.g_ncy = 0;
+    p.no_rows = (opt.keep == KEEP_NOTHING && fused_grid) ? 1 : 0;
+    if (fused_grid) {
+        p.g_count = (unsigned long long *)grid->count;
+        p.g_fx = (unsigned long long *)grid->fx;
+        p.g_fy = (unsigned long long *)grid->fy;
+        p.g_dlon = grid->dlon;
+        p.g_dlat = grid->dlat;
+        p.g_ncx = grid->ncx;
+        p.g_ncy = grid->ncy;
+    }
 
     // 3. launch: static slots, prepare, persistent integrator (one wave of resident blocks)
     bool strict = (flags & RWRT_MODE_STRICT) != 0;
@@ -620,8 +692,12 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     p.coop = coop ? 1 : 0;
     if (!coop || nlive == 0) use_records = false;   // the record layout is a mode of the cooperative kernel
     if (hx && !use_records) return RWRT_HX_UNSUPPORTED;
+    if (!coop && (grid || opt.keep != KEEP_PLANES))
+        return fail(RWRT_ERR_ARG, "ray records / gridding sweeps need the cooperative-gather kernel (fields of < 2^30 points, "
+                                  "RWRT_PER_LANE_GATHER unset)");
     p.rec = nullptr;
     p.rec_rows = 0;
+    p.rec_it0 = 1;
     p.rows_done = nullptr;
     p.inv = nullptr;
     int per_sm = strict ? occupancy_rk45_strict(coop) : occupancy_rk45_fast(coop);
@@ -635,7 +711,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     if (integrate_blocks < 1) integrate_blocks = 1;
     int prepare_blocks = (int)(((long long)nlive + 127) / 128);
     int fill_blocks = (int)((N + 255) / 256);
-    if (!coop || nwin < 1) nwin = 1;               // only the cooperative kernel can park rays at a window end
+    if (!coop || nwin < 1 || opt.keep == KEEP_RECORDS) nwin = 1;   // only the cooperative kernel can park rays at a window end
     if (nwin > nt - 1) nwin = nt - 1;
     if (use_records) {
         // the records of one time window must fit beside everything else: more windows when memory is short
@@ -653,6 +729,9 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         int max_rows = (int)(budget / per_row < 2147483647ull ? budget / per_row : 2147483647ull);
         if (max_rows < 2) return fail(RWRT_ERR_NOMEM, "no room for the ray records (%llu rays): shard the sources", nlive);
         int need_win = (nt - 1 + (max_rows - 1) - 1) / (max_rows - 1);
+        if (need_win > nwin && opt.keep == KEEP_RECORDS)
+            return fail(RWRT_ERR_NOMEM, "the ray records of the whole run (%llu rays x %d rows x 64 B) do not fit on the device: "
+                                        "shard the sources, or use rwrt_ray_run_rk45 / rwrt_ray_sweep_grid (time windows)", nlive, nt - 1);
         if (need_win > nwin) nwin = need_win;
         if (nwin > nt - 1) nwin = nt - 1;
         int rows = (nt - 1 + nwin - 1) / nwin + (hx ? 0 : 1);  // rows of the largest window (the host path copies whole buffers: no slack row)
@@ -705,12 +784,25 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     for (int w = 0; w < nwin; ++w) {
         p.it_begin = bounds[w];
         p.it_end = bounds[w + 1];
+        p.rec_it0 = p.it_begin;                     // record row r of this window is output row it_begin + r
         if (w > 0) CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));  // rewind the work queue
+        cudaEvent_t *we = win_events(h, w);
+        if (we) CU(cudaEventRecord(we[0], s));
         if (strict) launch_rk45_window_strict(p, integrate_blocks, s);
         else launch_rk45_window_fast(p, integrate_blocks, s);
         CU(cudaGetLastError());
+        if (we) {
+            CU(cudaEventRecord(we[1], s));
+            h->n_win_timed = w + 1;
+        }
         ++launches;
-        if (use_records && !(hx && hx->row0_only)) {   // rows [it_begin, it_end) of the reference layout from the records
+        if (grid && grid->from_records && use_records) {   // the window's records -> ray-density / flux grids
+            launch_grid_records(p.rec, p.rec_rows, p.rows_done, p.nlive, p.it_begin, p.it_end, grid->dlon, grid->dlat, grid->ncx,
+                                grid->ncy, grid->count, grid->fx, grid->fy, h->sm_count, s);
+            CU(cudaGetLastError());
+            ++launches;
+        }
+        if (use_records && !row0_only) {   // rows [it_begin, it_end) of the reference layout from the records
             if (strict) launch_expand_records_strict(p, s);
             else launch_expand_records_fast(p, s);
             CU(cudaGetLastError());
@@ -731,6 +823,16 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     h->last_nlive = (double)nlive;
     if (total_accepted)
         CU(cudaMemcpyAsync(total_accepted, ctr + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    if (opt.keep == KEEP_RECORDS && use_records) {
+        h->last_p = p;
+        h->last_p.it_begin = 1;
+        h->last_p.it_end = nt;
+        h->last_p.accepted = nullptr;                // caller memory: not touched again after this call
+        h->last_p.attempts = nullptr;
+        h->last_p.status = nullptr;
+        h->last_strict = strict;
+        h->have_records = true;
+    }
     return RWRT_OK;
 }
 
@@ -986,8 +1088,10 @@ int rwrt_ray_run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int
 {
     int nwin = 1;
     if (const char *e = getenv("RWRT_WINDOWS")) nwin = atoi(e);  // tuning / testing: split the run into time windows
+    RunOpts o;
+    o.nwin = nwin;
     return run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7,
-                    accepted, attempts, status, total_accepted, stream, nwin, nullptr, nullptr);
+                    accepted, attempts, status, total_accepted, stream, o);
 }
 
 int rwrt_trim(rwrt_handle h)
@@ -998,6 +1102,8 @@ int rwrt_trim(rwrt_handle h)
     h->records.release();
     h->packed.release();
     h->direct.release();
+    h->row0.release();
+    h->have_records = false;
     h->rows_done.release();
     h->inv.release();
     h->state.release();
@@ -1020,6 +1126,28 @@ int rwrt_last_run_stats(rwrt_handle h, double *stats3)
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         stats3[2] = ms;
     }
+    return RWRT_OK;
+}
+
+int rwrt_last_run_times(rwrt_handle h, double *ms4)
+{
+    if (!h || !ms4) return fail(RWRT_ERR_ARG, "rwrt_last_run_times: NULL argument");
+    ms4[0] = ms4[1] = ms4[2] = ms4[3] = 0;
+    if (!h->timed) return RWRT_OK;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    ms4[0] = ms;
+    for (int w = 0; w < h->n_win_timed; ++w) {
+        CU(cudaEventElapsedTime(&ms, h->ev_win[2 * w], h->ev_win[2 * w + 1]));
+        ms4[1] += ms;
+    }
+    if (h->n_win_timed > 0) {
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev_win[0]));
+        ms4[2] = ms;
+    }
+    ms4[3] = ms4[0] - ms4[1] - ms4[2];
     return RWRT_OK;
 }
 
@@ -1047,6 +1175,133 @@ int rwrt_grid_accumulate(rwrt_handle h, int64_t nslot, int nt, const double *out
     CU(cudaSetDevice(h->device));
     launch_grid_accumulate(nslot, nt, out7, dlon_deg, dlat_deg, ncx, ncy, (long long *)count, (long long *)fx,
                            (long long *)fy, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return RWRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grid-only sweep and device-resident ray records
+// ---------------------------------------------------------------------------------------------
+static int check_grid(const char *who, double dlon_deg, double dlat_deg, int ncx, int ncy, const int64_t *count, const int64_t *fx,
+                      const int64_t *fy)
+{
+    if (!count || !fx || !fy || ncx < 1 || ncy < 1 || !(dlon_deg > 0) || !(dlat_deg > 0))
+        return fail(RWRT_ERR_ARG, "%s: bad grid argument", who);
+    if ((long long)ncx * ncy > 2147483647LL) return fail(RWRT_ERR_ARG, "%s: more than 2^31-1 grid cells", who);
+    return RWRT_OK;
+}
+
+int rwrt_ray_sweep_grid(rwrt_handle h, int nsource, const double *src_lon, const double *src_lat, const int32_t *src_member,
+                        int nzwn, const double *zwn, double freq, int nt, double tstep, double ttotal, double rtol, double atol,
+                        double min_step_factor, double cut_off, uint32_t flags, double dlon_deg, double dlat_deg, int ncx,
+                        int ncy, int64_t *count, int64_t *fx, int64_t *fy, int64_t *accepted, int8_t *status,
+                        int64_t *total_accepted, void *stream)
+{
+    if (!h || nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_ray_sweep_grid: bad sizes");
+    int rc = check_grid("rwrt_ray_sweep_grid", dlon_deg, dlat_deg, ncx, ncy, count, fx, fy);
+    if (rc) return rc;
+    if (!h->ready) return fail(RWRT_ERR_STATE, "rwrt_ray_sweep_grid before rwrt_bs_ready");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->device));
+    const long long N = 3LL * nsource * nzwn;
+    if (N == 0) {
+        if (total_accepted) CU(cudaMemsetAsync(total_accepted, 0, sizeof(int64_t), s));
+        return RWRT_OK;
+    }
+    // the t = 0 state (wr.py:344-395) is all a sweep keeps of the seven planes: 7 x N doubles on the handle
+    if (h->row0.reserve((size_t)7 * N * sizeof(double))) return fail(RWRT_ERR_NOMEM, "t = 0 state (%lld slots)", N);
+    rc = rwrt_ray_init(h, nsource, src_lon, src_lat, src_member, nzwn, zwn, freq, 1, (double *)h->row0.p, stream);
+    if (rc) return rc;
+    // slots without a real root count zero steps / status 0 (expand_records writes these on the trajectory path)
+    if (accepted) CU(cudaMemsetAsync(accepted, 0, (size_t)N * sizeof(int64_t), s));
+    if (status) CU(cudaMemsetAsync(status, 0, (size_t)N, s));
+    GridSpec g;
+    g.dlon = dlon_deg;
+    g.dlat = dlat_deg;
+    g.ncx = ncx;
+    g.ncy = ncy;
+    g.count = (long long *)count;
+    g.fx = (long long *)fx;
+    g.fy = (long long *)fy;
+    g.from_records = (flags & RWRT_GRID_FROM_RECORDS) != 0;
+    RunOpts o;
+    o.grid = &g;
+    o.keep = KEEP_NOTHING;
+    if (const char *e = getenv("RWRT_WINDOWS")) o.nwin = atoi(e);
+    return run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags,
+                    (double *)h->row0.p, accepted, nullptr, status, total_accepted, stream, o);
+}
+
+int rwrt_ray_run_rk45_records(rwrt_handle h, int nsource, const int32_t *src_member, int nzwn, int nt, double tstep,
+                              double ttotal, double rtol, double atol, double min_step_factor, double cut_off, uint32_t flags,
+                              const double *out7_row0, int64_t *accepted, int64_t *attempts, int8_t *status,
+                              int64_t *total_accepted, void *stream)
+{
+    if (!h || nsource < 0 || nzwn < 0 || nt < 1) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45_records: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(h->device));
+    const long long N = 3LL * nsource * nzwn;
+    if (N > 0 && !out7_row0) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45_records: out7_row0 is NULL");
+    if (N > 0) {
+        // the handle keeps its own copy of the t = 0 row: rwrt_records_expand reads the constant rows of the slots
+        // without a root from it long after the caller's buffer may be gone
+        if (h->row0.reserve((size_t)7 * N * sizeof(double))) return fail(RWRT_ERR_NOMEM, "t = 0 state (%lld slots)", N);
+        CU(cudaMemcpyAsync(h->row0.p, out7_row0, (size_t)7 * N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        if (accepted) CU(cudaMemsetAsync(accepted, 0, (size_t)N * sizeof(int64_t), s));
+        if (attempts) CU(cudaMemsetAsync(attempts, 0, (size_t)N * sizeof(int64_t), s));
+        if (status) CU(cudaMemsetAsync(status, 0, (size_t)N, s));
+    }
+    RunOpts o;
+    o.keep = KEEP_RECORDS;
+    return run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags,
+                    (double *)h->row0.p, accepted, attempts, status, total_accepted, stream, o);
+}
+
+int rwrt_records_info(rwrt_handle h, int64_t *nray, int *rec_rows, const double **rec, const int32_t **rows_done,
+                      const int32_t **ray_slot, const int32_t **slot_to_ray)
+{
+    if (!h) return fail(RWRT_ERR_ARG, "rwrt_records_info: null handle");
+    if (!h->have_records) return fail(RWRT_ERR_STATE, "rwrt_records_info: no ray records on the handle (run rwrt_ray_run_rk45_records)");
+    const RunParams &p = h->last_p;
+    if (nray) *nray = p.nlive;
+    if (rec_rows) *rec_rows = p.rec_rows;
+    if (rec) *rec = p.rec;
+    if (rows_done) *rows_done = p.rows_done;
+    if (ray_slot) *ray_slot = p.live;
+    if (slot_to_ray) *slot_to_ray = p.inv;
+    return RWRT_OK;
+}
+
+int rwrt_records_expand(rwrt_handle h, int row_begin, int row_end, double *dst7, void *stream)
+{
+    if (!h || !dst7) return fail(RWRT_ERR_ARG, "rwrt_records_expand: NULL argument");
+    if (!h->have_records) return fail(RWRT_ERR_STATE, "rwrt_records_expand: no ray records on the handle");
+    RunParams q = h->last_p;
+    if (row_begin < 1 || row_end > q.nt || row_end < row_begin)
+        return fail(RWRT_ERR_ARG, "rwrt_records_expand: rows [%d, %d) outside [1, %d)", row_begin, row_end, q.nt);
+    CU(cudaSetDevice(h->device));
+    q.it_begin = row_begin;
+    q.it_end = row_end;
+    q.dst = dst7;
+    q.dst_pl = (size_t)q.N * (size_t)(row_end - row_begin);
+    q.dst_it0 = row_begin;
+    if (h->last_strict) launch_expand_records_strict(q, (cudaStream_t)stream);
+    else launch_expand_records_fast(q, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return RWRT_OK;
+}
+
+int rwrt_grid_accumulate_records(rwrt_handle h, double dlon_deg, double dlat_deg, int ncx, int ncy, int64_t *count, int64_t *fx,
+                                 int64_t *fy, void *stream)
+{
+    if (!h) return fail(RWRT_ERR_ARG, "rwrt_grid_accumulate_records: null handle");
+    int rc = check_grid("rwrt_grid_accumulate_records", dlon_deg, dlat_deg, ncx, ncy, count, fx, fy);
+    if (rc) return rc;
+    if (!h->have_records) return fail(RWRT_ERR_STATE, "rwrt_grid_accumulate_records: no ray records on the handle");
+    const RunParams &p = h->last_p;
+    CU(cudaSetDevice(h->device));
+    launch_grid_records(p.rec, p.rec_rows, p.rows_done, p.nlive, 1, p.nt, dlon_deg, dlat_deg, ncx, ncy, (long long *)count,
+                        (long long *)fx, (long long *)fy, h->sm_count, (cudaStream_t)stream);
     CU(cudaGetLastError());
     return RWRT_OK;
 }
@@ -1161,8 +1416,11 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
         hx.copy_stream = copy_stream;
         hx.row0_only = false;
         hx_configure(&hx);
+        RunOpts o;
+        o.nwin = nwin;
+        o.hx = &hx;
         rc = run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7,
-                      accepted, attempts, status, total_accepted, stream, nwin, nullptr, nullptr, &hx);
+                      accepted, attempts, status, total_accepted, stream, o);
         if (rc == RWRT_OK) {
             if (cudaStreamSynchronize(s) != cudaSuccess || cudaStreamSynchronize(copy_stream) != cudaSuccess)
                 rc = fail(RWRT_ERR_CUDA, "rwrt_ray_run_rk45_d2h: stream synchronisation failed");
@@ -1182,8 +1440,12 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
         ctx.first = true;
         CU(cudaEventCreateWithFlags(&ctx.ev[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx.ev[1], cudaEventDisableTiming));
+        RunOpts o;
+        o.nwin = nwin;
+        o.hook = host_copy_hook;
+        o.hook_ctx = &ctx;
         rc = run_rk45(h, nsource, src_member, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags, out7,
-                      accepted, attempts, status, total_accepted, stream, nwin, host_copy_hook, &ctx);
+                      accepted, attempts, status, total_accepted, stream, o);
         if (rc == RWRT_OK && ctx.first && nout > 0 && out7) {
             cudaError_t e = cudaMemcpyAsync(out7_host, out7, nout * 8, cudaMemcpyDeviceToHost, s);
             if (e != cudaSuccess) rc = fail(RWRT_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
@@ -1290,9 +1552,14 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
         rc = rwrt_ray_init(h, nsource, (const double *)(arena + o_slon), (const double *)(arena + o_slat), dmem, nzwn,
                            (const double *)(arena + o_zwn), freq, use_hx ? 1 : nt, (double *)(arena + o_out), s);
         if (rc) goto done;
+        RunOpts o;
+        o.nwin = nwin;
+        o.hook = use_hx ? nullptr : host_copy_hook;
+        o.hook_ctx = &ctx;
+        o.hx = use_hx ? &hx : nullptr;
         rc = run_rk45(h, nsource, dmem, nzwn, nt, tstep, ttotal, rtol, atol, min_step_factor, cut_off, flags,
                       (double *)(arena + o_out), (int64_t *)(arena + o_acc), nullptr, (int8_t *)(arena + o_st),
-                      (int64_t *)(arena + o_tot), s, nwin, use_hx ? nullptr : host_copy_hook, &ctx, use_hx ? &hx : nullptr);
+                      (int64_t *)(arena + o_tot), s, o);
         if (rc) goto done;      // RWRT_HX_UNSUPPORTED included: the caller runs the device-side expansion instead
     }
     if (!use_hx && ctx.first && nout > 0)  // nothing was integrated (no live ray / nt == 1): plain copy of what there is

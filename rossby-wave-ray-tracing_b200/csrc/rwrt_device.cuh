@@ -456,6 +456,35 @@ __device__ __forceinline__ double haversine(double lon_c, double lat_c, double l
 }
 
 
+// Ray-density / wave-ray-flux gridding of one output sample (this project's definition, oracle/gridding.py; the
+// reference ships no gridding code -- the manual's tool would read rlon, rlat, rug, rvg as wr.py:947-959 writes
+// them).  Every operation is an individually rounded IEEE op (intrinsics: no FMA contraction in any build), so the
+// cell index equals NumPy's floor((lon * rad2deg + 360) / dlon) bit for bit wherever this is inlined.
+// Returns the flattened cell ix * ncy + iy, or -1 when the sample is not counted.
+__device__ __forceinline__ long long grid_cell(double lon, double lat, double l, double dlon, double dlat, int ncx,
+                                               int ncy)
+{
+    if (!(lon == lon) || !(lat == lat) || !(l == l)) return -1;
+    const double rad2deg = 1.0 / (PI / 180.0);  // constants.py:14-15
+    const double x = __ddiv_rn(__dadd_rn(__dmul_rn(lon, rad2deg), 360.0), dlon);
+    const double y = __ddiv_rn(__dadd_rn(__dmul_rn(lat, rad2deg), 90.0), dlat);
+    const double fxd = floor(x), fyd = floor(y);
+    if (!(fxd >= 0.0) || !(fxd < (double)ncx) || !(fyd >= 0.0)) return -1;
+    const int ix = (int)fxd, iy = (int)fmin(fyd, (double)(ncy - 1));
+    return (long long)ix * ncy + iy;
+}
+// count += 1; flux += rint(ug|vg * 2^20) as int64 fixed point: integer sums are order independent, so the grids are
+// bit-identical for any sharding of the rays over GPUs and any accumulation order.  Results unused: RED, not ATOM.
+__device__ __forceinline__ void grid_add(unsigned long long *count, unsigned long long *fx, unsigned long long *fy,
+                                         long long c, double ug, double vg)
+{
+    atomicAdd(count + c, 1ULL);
+    if (ug == ug && vg == vg) {
+        atomicAdd(fx + c, (unsigned long long)llrint(ug * 1048576.0));
+        atomicAdd(fy + c, (unsigned long long)llrint(vg * 1048576.0));
+    }
+}
+
 // FAST build of the speed cut-off test |2 atan2(sqrt a, sqrt(1-a))| >= cut (wr.py:97-112, 844-850):
 // the central angle is monotonic in a on [0, pi], so compare a with sin^2(cut/2); cos of both latitudes
 // are already known (cos_c from the last stage, cos_p cached from the previous output).

@@ -19,23 +19,33 @@ __global__ void __launch_bounds__(256) grid_kernel(long long nslot, int nt, cons
                                                    unsigned long long *fy)
 {
     long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int it = blockIdx.y + 1;
-    if (slot >= nslot || it >= nt) return;
-    const size_t pl = (size_t)nt * nslot, o = (size_t)it * nslot + slot;
-    double lon = out[o], lat = out[pl + o], l = out[3 * pl + o];
-    if (!(lon == lon) || !(lat == lat) || !(l == l)) return;
-    const double rad2deg = 1.0 / (PI / 180.0);  // constants.py:14-15
-    double x = (lon * rad2deg + 360.0) / dlon, y = (lat * rad2deg + 90.0) / dlat;
-    double fxd = floor(x), fyd = floor(y);
-    if (!(fxd >= 0.0) || !(fxd < (double)ncx) || !(fyd >= 0.0)) return;
-    int ix = (int)fxd, iy = (int)fmin(fyd, (double)(ncy - 1));
-    size_t c = (size_t)ix * ncy + iy;
-    double ug = out[5 * pl + o], vg = out[6 * pl + o];
-    atomicAdd(count + c, 1ULL);
-    if (ug == ug && vg == vg) {
-        long long qx = llrint(ug * 1048576.0), qy = llrint(vg * 1048576.0);
-        atomicAdd(fx + c, (unsigned long long)qx);
-        atomicAdd(fy + c, (unsigned long long)qy);
+    if (slot >= nslot) return;
+    const size_t pl = (size_t)nt * nslot;
+    for (int it = blockIdx.y + 1; it < nt; it += gridDim.y) {      // gridDim.y is capped at 65535 rows per pass
+        const size_t o = (size_t)it * nslot + slot;
+        const long long c = grid_cell(out[o], out[pl + o], out[3 * pl + o], dlon, dlat, ncx, ncy);
+        if (c >= 0) grid_add(count, fx, fy, c, out[5 * pl + o], out[6 * pl + o]);
+    }
+}
+
+// The same accumulation from the per-ray records the integrator writes (rec[ray][row][8] = lon, lat, k, l, A, ug, vg,
+// pad; rows [it_begin, min(it_end, rows_done[ray])) are valid): no (7, nt, N) planes are needed, so a sweep that only
+// wants the grids never expands its records.  One thread per (ray, row): a warp reads 2 KB of contiguous records.
+__global__ void __launch_bounds__(256) grid_records_kernel(const double *rec, int rec_rows, const int32_t *rows_done,
+                                                           long long nlive, int it_begin, int it_end, double dlon,
+                                                           double dlat, int ncx, int ncy, unsigned long long *count,
+                                                           unsigned long long *fx, unsigned long long *fy)
+{
+    const int len = it_end - it_begin;
+    const long long total = nlive * (long long)len;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long ray = i / len;
+        const int r = (int)(i - ray * len);
+        if (it_begin + r >= rows_done[ray]) continue;              // the ray died before this row (wr.py:838-855)
+        const double2 *q = reinterpret_cast<const double2 *>(rec + ((size_t)ray * rec_rows + r) * 8);
+        const double2 a = __ldcs(q), b = __ldcs(q + 1), c2 = __ldcs(q + 2), d = __ldcs(q + 3);
+        const long long c = grid_cell(a.x, a.y, b.y, dlon, dlat, ncx, ncy);
+        if (c >= 0) grid_add(count, fx, fy, c, c2.y, d.x);
     }
 }
 
@@ -45,9 +55,23 @@ void launch_grid_accumulate(long long nslot, int nt, const double *out7, double 
                             int ncy, long long *count, long long *fx, long long *fy, cudaStream_t s)
 {
     if (nslot <= 0 || nt < 2) return;
-    dim3 grid((unsigned)((nslot + 255) / 256), nt - 1);
+    dim3 grid((unsigned)((nslot + 255) / 256), (unsigned)(nt - 1 < 65535 ? nt - 1 : 65535));
     grid_kernel<<<grid, 256, 0, s>>>(nslot, nt, out7, dlon_deg, dlat_deg, ncx, ncy, (unsigned long long *)count,
                                      (unsigned long long *)fx, (unsigned long long *)fy);
+}
+
+void launch_grid_records(const double *rec, int rec_rows, const int32_t *rows_done, long long nlive, int it_begin, int it_end,
+                         double dlon_deg, double dlat_deg, int ncx, int ncy, long long *count, long long *fx, long long *fy,
+                         int sm_count, cudaStream_t s)
+{
+    const long long total = nlive * (long long)(it_end - it_begin);
+    if (total <= 0) return;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count * 64;                // grid-stride beyond a few waves
+    if (blocks > cap) blocks = cap;
+    grid_records_kernel<<<(unsigned)blocks, 256, 0, s>>>(rec, rec_rows, rows_done, nlive, it_begin, it_end, dlon_deg, dlat_deg,
+                                                          ncx, ncy, (unsigned long long *)count, (unsigned long long *)fx,
+                                                          (unsigned long long *)fy);
 }
 
 }  // namespace rwrt

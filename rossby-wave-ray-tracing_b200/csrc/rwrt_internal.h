@@ -50,6 +50,10 @@ void launch_sample18(const Grid &g, const double *f18, long long n, const double
 void launch_grid_accumulate(long long nslot, int nt, const double *out7, double dlon_deg, double dlat_deg, int ncx,
                             int ncy, long long *count, long long *fx, long long *fy, cudaStream_t s);
 
+void launch_grid_records(const double *rec, int rec_rows, const int32_t *rows_done, long long nlive, int it_begin, int it_end,
+                         double dlon_deg, double dlat_deg, int ncx, int ncy, long long *count, long long *fx, long long *fy,
+                         int sm_count, cudaStream_t s);
+
 int measure_fp64_peak(int sm_count, double *tflops, cudaStream_t s);
 
 // rwrt_api.cu helpers

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256, RWRT_EX_MINBLOCKS) expand_records(RunPara
             for (int h = 0; h < H; ++h) {
                 const int it = row0 + rr + 8 * h;
                 v[q][h] = make_double2(n, n);
-                if (it < rd[q]) v[q][h] = __ldcs(rec[q] + (size_t)(it - p.it_begin) * 4);
+                if (it < rd[q]) v[q][h] = __ldcs(rec[q] + (size_t)(it - p.rec_it0) * 4);
             }
     };
     request(block_row0);
@@ -657,6 +657,10 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src, u
         asm volatile("cp.async.commit_group;\n" ::);                                                                 \
     }
 
+// OUT: what happens to an output row -- OUT_ROWS (stored: record or planes; the product path of rwrt_ray_run_rk45),
+// OUT_GRID (added to the ray-density / flux grids: rwrt_ray_sweep_grid, no trajectory is materialised at all), or both.
+// Separate instantiations: the grid arithmetic (two fp64 divisions per output row) stays out of the plain kernel.
+template <int OUT>
 __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_coop(RunParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -963,14 +967,20 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
                 ug = gv.x;
                 vg = gv.y;
             }
-            if (p.rec) {  // record layout: 64 contiguous bytes per (ray, row), four 16-byte stores
-                double2 *r = reinterpret_cast<double2 *>(p.rec + ((size_t)my_ray * p.rec_rows + (L.it - p.it_begin)) * 8);
-                r[0] = make_double2(L.y[0], L.y[1]);
-                r[1] = make_double2(L.y[2], L.y[3]);
-                r[2] = make_double2(L.y[4], ug);
-                r[3] = make_double2(vg, 0.0);   // plain stores: streaming (.cs) ones measured the same
-            } else {
-                write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
+            if (OUT & OUT_ROWS) {
+                if (p.rec) {  // record layout: 64 contiguous bytes per (ray, row), four 16-byte stores
+                    double2 *r = reinterpret_cast<double2 *>(p.rec + ((size_t)my_ray * p.rec_rows + (L.it - p.rec_it0)) * 8);
+                    r[0] = make_double2(L.y[0], L.y[1]);
+                    r[1] = make_double2(L.y[2], L.y[3]);
+                    r[2] = make_double2(L.y[4], ug);
+                    r[3] = make_double2(vg, 0.0);   // plain stores: streaming (.cs) ones measured the same
+                } else {
+                    write_row(p, L.slot, L.it, L.y[0], L.y[1], L.y[2], L.y[3], L.y[4], ug, vg);
+                }
+            }
+            if (OUT & OUT_GRID) {  // the sample (lon, lat, l, ug, vg) of this row, exactly as a stored row would hold it
+                const long long cell = grid_cell(L.y[0], L.y[1], L.y[3], p.g_dlon, p.g_dlat, p.g_ncx, p.g_ncy);
+                if (cell >= 0) grid_add(p.g_count, p.g_fx, p.g_fy, cell, ug, vg);
             }
             L.plon = L.y[0];
             L.plat = L.y[1];

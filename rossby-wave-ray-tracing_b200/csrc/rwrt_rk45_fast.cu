@@ -9,7 +9,7 @@ void launch_rk45_setup_fast(const RunParams &p, int prepare_blocks, int fill_blo
 {
     if (p.nlive > 0) fast::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
     // The constant rows of NaN-root slots touch no slot the integrator writes: low-priority side stream.
-    if (p.N > 0 && p.nt > 1 && !p.rec)   // record layout: expand_records writes every row instead
+    if (p.N > 0 && p.nt > 1 && !p.rec && !p.no_rows)   // record layout: expand_records writes every row instead; sweep: no rows at all
         fast::fill_static_slots<<<dim3(fill_blocks, p.nt - 1 < 24 ? p.nt - 1 : 24), 256, 0, aux>>>(p);
 }
 void launch_expand_records_fast(const RunParams &p, cudaStream_t s)
@@ -24,9 +24,15 @@ void launch_expand_records_fast(const RunParams &p, cudaStream_t s)
 void launch_rk45_window_fast(const RunParams &p, int integrate_blocks, cudaStream_t s)
 {
     if (p.nlive <= 0) return;
-    if (p.coop)
-        fast::rk45_integrate_coop<<<integrate_blocks, fast::RK_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
-    else
+    if (p.coop) {
+        const bool grid = p.g_count != nullptr;
+        if (p.no_rows && grid)
+            fast::rk45_integrate_coop<OUT_GRID><<<integrate_blocks, fast::RK_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
+        else if (grid)
+            fast::rk45_integrate_coop<OUT_ROWS | OUT_GRID><<<integrate_blocks, fast::RK_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
+        else
+            fast::rk45_integrate_coop<OUT_ROWS><<<integrate_blocks, fast::RK_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
+    } else
         fast::rk45_integrate<<<integrate_blocks, fast::RK_THREADS, fast::RK_SMEM_BYTES, s>>>(p);
 }
 void launch_rk4_fast(const RunParams &p, cudaStream_t s)
@@ -44,8 +50,10 @@ int occupancy_rk45_fast(bool coop)
 {
     int nb = 0;
     if (coop) {
-        cudaFuncSetAttribute(fast::rk45_integrate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::CO_SMEM_BYTES);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast::rk45_integrate_coop, fast::RK_THREADS, fast::CO_SMEM_BYTES);
+        cudaFuncSetAttribute(fast::rk45_integrate_coop<OUT_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::CO_SMEM_BYTES);
+        cudaFuncSetAttribute(fast::rk45_integrate_coop<OUT_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::CO_SMEM_BYTES);
+        cudaFuncSetAttribute(fast::rk45_integrate_coop<OUT_ROWS | OUT_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::CO_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast::rk45_integrate_coop<OUT_ROWS>, fast::RK_THREADS, fast::CO_SMEM_BYTES);
 #if RWRT_TMEM_KS
         // the occupancy calculator answers 1 for a kernel that allocates tensor memory (it cannot know how many
         // columns tcgen05.alloc will ask for); this build takes 64 of the 512 columns per block

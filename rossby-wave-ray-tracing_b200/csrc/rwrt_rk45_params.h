@@ -25,6 +25,7 @@ struct RunParams {
     // expand_records turns them into the reference layout afterwards (no partial-sector stores)
     double *rec;                // (nlive, rec_rows, 8) or nullptr
     int rec_rows;               // rows per ray in `rec` (= rows of the largest time window)
+    int rec_it0;                // record row r of a ray holds output row rec_it0 + r (= it_begin of the window that wrote it)
     int32_t *rows_done;         // (nlive): number of valid rows 0..rows_done-1 of a ray so far
     const int32_t *inv;         // (N): slot -> index in the live list, -1 for NaN-root slots
     int it_begin, it_end;       // this launch produces output rows [it_begin, it_end) (time window)
@@ -33,6 +34,17 @@ struct RunParams {
     signed char *status;        // (N) or nullptr
     unsigned long long *queue;  // work-fetch counter
     unsigned long long *total_accepted;
+    // Gridding (rwrt_ray_sweep_grid): the cooperative integrator adds every output sample to the ray-density / flux
+    // grids as it produces it (three fire-and-forget integer RED per output row) -- or, with g_count == nullptr and
+    // records on, grid_records_kernel consumes the window's records afterwards.
+    unsigned long long *g_count, *g_fx, *g_fy;   // (g_ncx, g_ncy) each, or nullptr
+    double g_dlon, g_dlat;      // cell size in degrees
+    int g_ncx, g_ncy;
+    int no_rows;                // 1: no output rows are stored at all (grid-only sweep: neither records nor planes)
 };
+
+// What one instantiation of the cooperative integrator does with an output row
+constexpr int OUT_ROWS = 1;     // store it (64-byte record, or the seven planes directly)
+constexpr int OUT_GRID = 2;     // add it to the grids
 
 }  // namespace rwrt

@@ -9,7 +9,7 @@ void launch_rk45_setup_strict(const RunParams &p, int prepare_blocks, int fill_b
 {
     if (p.nlive > 0) strict::rk45_prepare<<<prepare_blocks, 128, 0, s>>>(p);
     // The constant rows of NaN-root slots touch no slot the integrator writes: low-priority side stream.
-    if (p.N > 0 && p.nt > 1 && !p.rec)   // record layout: expand_records writes every row instead
+    if (p.N > 0 && p.nt > 1 && !p.rec && !p.no_rows)   // record layout: expand_records writes every row instead; sweep: no rows at all
         strict::fill_static_slots<<<dim3(fill_blocks, p.nt - 1 < 24 ? p.nt - 1 : 24), 256, 0, aux>>>(p);
 }
 void launch_expand_records_strict(const RunParams &p, cudaStream_t s)
@@ -24,9 +24,15 @@ void launch_expand_records_strict(const RunParams &p, cudaStream_t s)
 void launch_rk45_window_strict(const RunParams &p, int integrate_blocks, cudaStream_t s)
 {
     if (p.nlive <= 0) return;
-    if (p.coop)
-        strict::rk45_integrate_coop<<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
-    else
+    if (p.coop) {
+        const bool grid = p.g_count != nullptr;
+        if (p.no_rows && grid)
+            strict::rk45_integrate_coop<OUT_GRID><<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
+        else if (grid)
+            strict::rk45_integrate_coop<OUT_ROWS | OUT_GRID><<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
+        else
+            strict::rk45_integrate_coop<OUT_ROWS><<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
+    } else
         strict::rk45_integrate<<<integrate_blocks, strict::RK_THREADS, strict::RK_SMEM_BYTES, s>>>(p);
 }
 void launch_rk4_strict(const RunParams &p, cudaStream_t s)
@@ -44,8 +50,10 @@ int occupancy_rk45_strict(bool coop)
 {
     int nb = 0;
     if (coop) {
-        cudaFuncSetAttribute(strict::rk45_integrate_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::CO_SMEM_BYTES);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, strict::rk45_integrate_coop, strict::RK_THREADS, strict::CO_SMEM_BYTES);
+        cudaFuncSetAttribute(strict::rk45_integrate_coop<OUT_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::CO_SMEM_BYTES);
+        cudaFuncSetAttribute(strict::rk45_integrate_coop<OUT_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::CO_SMEM_BYTES);
+        cudaFuncSetAttribute(strict::rk45_integrate_coop<OUT_ROWS | OUT_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::CO_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, strict::rk45_integrate_coop<OUT_ROWS>, strict::RK_THREADS, strict::CO_SMEM_BYTES);
 #if RWRT_TMEM_KS
         // the occupancy calculator answers 1 for a kernel that allocates tensor memory (it cannot know how many
         // columns tcgen05.alloc will ask for); this build takes 64 of the 512 columns per block

@@ -21,6 +21,21 @@ def shard_bounds(nsource: int, rank: int, world: int):
     return s0, s1
 
 
+def shard_indices(nsource: int, rank: int, world: int, mode: str = "block"):
+    """Source indices of `rank`.  "block": the contiguous block of `shard_bounds` (a rank's trajectories are a slice
+    of the source axis).  "stride": rank, rank + world, ... -- for grid-only sweeps, whose result does not depend on
+    which rank integrates which source; sources are ordered by latitude and the work per source varies with it, so
+    strided shards are balanced where latitude bands are not."""
+    if mode == "block":
+        s0, s1 = shard_bounds(nsource, rank, world)
+        return np.arange(s0, s1)
+    if mode == "stride":
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError("need 0 <= rank < world")
+        return np.arange(rank, int(nsource), world)
+    raise ValueError("mode must be 'block' or 'stride'")
+
+
 def allreduce_grids(*grids):
     """In-place sum of integer accumulator tensors over all ranks (no-op without a process group)."""
     import torch.distributed as dist
@@ -28,6 +43,25 @@ def allreduce_grids(*grids):
         for g in grids:
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
     return grids
+
+
+def sweep_sharded(make_wr, src_lon_deg, src_lat_deg, grid, rank=None, world=None, shard="stride", strict=False,
+                  from_records=False):
+    """Grid-only sweep of this rank's share of the sources (`gridding.sweep`: no trajectory arrays) followed by the
+    path's one collective: a single all-reduce (sum) of the (3, ncx, ncy) int64 accumulators.  Returns
+    dict(wr=..., indices=..., grids=all-reduced (3, ncx, ncy) tensor)."""
+    import torch.distributed as dist
+    from . import gridding
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    idx = shard_indices(len(src_lon_deg), rank, world, shard)
+    w = make_wr(len(idx))
+    w.set_source_array(np.asarray(src_lon_deg)[idx], np.asarray(src_lat_deg)[idx])
+    grids = gridding.sweep(w, grid[0], grid[1], strict=strict, from_records=from_records)
+    allreduce_grids(grids)
+    return {"wr": w, "indices": idx, "grids": grids}
 
 
 def run_sharded(make_wr, src_lon_deg, src_lat_deg, grid=None, rank=None, world=None, to_host=False):

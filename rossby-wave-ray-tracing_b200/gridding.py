@@ -38,6 +38,59 @@ def accumulate(wr, dlon_deg, dlat_deg, out=None):
     return count, fx, fy
 
 
+def new_grids(dlon_deg, dlat_deg, device):
+    """One zeroed (3, ncx, ncy) int64 tensor = count, fx, fy: a single contiguous buffer, so that the ranks of a
+    sharded sweep merge with ONE all-reduce (`dist.allreduce_grids(g)`)."""
+    import torch
+    ncx, ncy = grid_shape(dlon_deg, dlat_deg)
+    return torch.zeros((3, ncx, ncy), dtype=torch.int64, device=device)
+
+
+def sweep(wr, dlon_deg, dlat_deg, out=None, strict=False, from_records=False, want_accepted=True):
+    """Grid-only sweep (`rwrt_ray_sweep_grid`): t = 0 state + RK45 + gridding of `wr`'s sources in one pass with NO
+    trajectory arrays -- neither the (7, nt, N) planes the reference allocates up front (wr.py:157-167) nor ray
+    records: the integrator adds every output sample to the grids as it produces it (from_records=True: time
+    windows of ray records gridded by a second kernel -- same bits).  Returns the (3, ncx, ncy) int64 grids
+    (count, fx, fy), added into `out` when given.  Sets wr.total_accepted and, if want_accepted, wr.accepted / wr.status."""
+    import numpy as np
+    import torch
+    wr._check_ready()
+    dev = torch.device("cuda", wr.bs.device)
+    ncx, ncy = grid_shape(dlon_deg, dlat_deg)
+    if out is None:
+        out = new_grids(dlon_deg, dlat_deg, dev)
+    N = 3 * wr.nsource * wr.nzwn
+    d_lon = torch.from_numpy(np.ascontiguousarray(wr.source_lon, dtype=np.float64)).to(dev)
+    d_lat = torch.from_numpy(np.ascontiguousarray(wr.source_lat, dtype=np.float64)).to(dev)
+    d_zwn = torch.from_numpy(np.ascontiguousarray(wr.zwn, dtype=np.float64)).to(dev)
+    d_acc = torch.empty(N, dtype=torch.int64, device=dev) if want_accepted else None
+    d_status = torch.empty(N, dtype=torch.int8, device=dev) if want_accepted else None
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    flags = (_lib.MODE_STRICT if strict else _lib.MODE_FAST) | (_lib.GRID_FROM_RECORDS if from_records else 0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().rwrt_ray_sweep_grid(
+            wr.bs._h, wr.nsource, _lib.ptr(d_lon), _lib.ptr(d_lat), None, wr.nzwn, _lib.ptr(d_zwn), float(wr.freq[0]),
+            wr.nt, float(wr.tstep[0]), float(wr.ttotal), float(wr.rtol), float(wr.atol), float(wr.MinStepFactor),
+            float(wr.cut_off_factor), flags, float(dlon_deg), float(dlat_deg), ncx, ncy, _lib.ptr(out[0]), _lib.ptr(out[1]),
+            _lib.ptr(out[2]), _lib.ptr(d_acc), _lib.ptr(d_status), _lib.ptr(d_total), _lib.stream_ptr()),
+            "rwrt_ray_sweep_grid")
+        wr.total_accepted = int(d_total.item())
+    if want_accepted:
+        shp = (3, wr.nsource, wr.nzwn)
+        wr.accepted = d_acc.cpu().numpy().reshape(shp)
+        wr.status = d_status.cpu().numpy().reshape(shp)
+    return out
+
+
+def checksum(grids):
+    """Order-independent 64-bit fingerprint of integer grids (sum of value * (2 * index + 1), wrapping): equal across
+    any sharding of the rays iff the reduced grids are equal (bench.py prints it per GPU count)."""
+    import torch
+    g = grids.reshape(-1)
+    w = torch.arange(g.numel(), dtype=torch.int64, device=g.device) * 2 + 1
+    return int((g * w).sum().item()) & 0xFFFFFFFFFFFFFFFF
+
+
 def flux(count, fx, fy):
     """Mean group velocity per cell (m/s) from the integer accumulators (NaN where no ray passed)."""
     import torch

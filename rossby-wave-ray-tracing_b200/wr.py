@@ -55,6 +55,7 @@ class WR:
         self.total_accepted = 0
         self._host = None
         self._host_t = None
+        self._host_stale = False     # d_out holds results that the host planes do not (ray_run(..., to_host=False))
         self.pin_results = False     # result planes in pinned host memory (see _host_planes)
 
     # ---- result arrays: allocated on first use (the reference allocates them in __init__) ----
@@ -81,6 +82,10 @@ class WR:
 
     def __getattr__(self, name):
         if name in NAMES:
+            # results that exist only on the GPU (ray_run(to_host=False), dist.run_sharded's default) are fetched on
+            # first access -- never the NaN pre-fill of wr.py:160-167 while d_out holds a newer run
+            if self.__dict__.get("_host_stale") and self.__dict__.get("d_out") is not None:
+                self.to_host()
             return self._host_planes()[NAMES.index(name)]
         raise AttributeError(name)
 
@@ -224,6 +229,7 @@ class WR:
             self.total_accepted = 0
             self.accepted = None
         self.status = self._d_status.cpu().numpy().reshape(shp)
+        self._host_stale = not delivered
         if to_host and not delivered:
             self.to_host()
 
@@ -232,8 +238,11 @@ class WR:
         import torch
         host = self._host_planes(fill=False)
         dst = self._host_t if self._host_t is not None else torch.from_numpy(host)
+        if self.d_out is None:
+            raise RuntimeError("no results on the GPU: call ray_run first (or the results were released by clean())")
         dst.copy_(self.d_out, non_blocking=self._host_t is not None)
         torch.cuda.synchronize(self.bs.device)
+        self._host_stale = False
         return host
 
     def output(self, ncfile):
@@ -243,6 +252,11 @@ class WR:
                            {n: getattr(self, n) for n in NAMES}, rad2deg)
 
     def clean(self):
+        if self._host_stale and self.d_out is not None:
+            import warnings
+            warnings.warn("WR.clean(): the results of the last ray_run(to_host=False) were never copied to the host "
+                          "and are released now", RuntimeWarning, stacklevel=2)
+        self._host_stale = False
         self.bs.clean()
         self.d_out = None
         self._host = None

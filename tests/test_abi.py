@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(L):
     assert set(syms) == set(lib.SYMBOLS)
     for s in syms:
         assert hasattr(L, s), s
-    assert L.rwrt_abi_version() == 1
+    assert L.rwrt_abi_version() == 2      # 2: sweep / records entry points (round 2)
 
 
 def test_no_compute_without_gpu(L):

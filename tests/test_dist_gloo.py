@@ -29,6 +29,22 @@ def test_shard_bounds_partition():
         rdist.shard_bounds(10, 2, 2)
 
 
+def test_shard_indices_partition():
+    for n in (0, 1, 7, 555840):
+        for world in (1, 2, 8):
+            for mode in ("block", "stride"):
+                parts = [rdist.shard_indices(n, r, world, mode) for r in range(world)]
+                allidx = np.sort(np.concatenate(parts)) if parts else np.zeros(0)
+                assert np.array_equal(allidx, np.arange(n))
+                sizes = [len(p) for p in parts]
+                assert max(sizes) - min(sizes) <= 1
+    assert np.array_equal(rdist.shard_indices(10, 1, 3, "stride"), [1, 4, 7])
+    s0, s1 = rdist.shard_bounds(10, 1, 3)
+    assert np.array_equal(rdist.shard_indices(10, 1, 3, "block"), np.arange(s0, s1))
+    with pytest.raises(ValueError):
+        rdist.shard_indices(10, 0, 2, "zigzag")
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -50,6 +66,12 @@ def _worker(rank, world, port, q):
     rdist.allreduce_grids(*grids)
     steps = torch.tensor([int(acc.sum())])
     dist.all_reduce(steps)
+    # the sweep's form: strided shards, count / fx / fy in ONE (3, ncx, ncy) buffer, one all-reduce
+    idx = rdist.shard_indices(len(sl), rank, world, "stride")
+    tr2, _ = parity.oracle_run(u, v, np.radians(sl[idx]), np.radians(sa[idx]), zwn, 6.0)
+    g3 = torch.from_numpy(np.stack(ogrid.accumulate(np.stack([tr2[n] for n in parity.NAMES]), 2.5, 2.5)))
+    rdist.allreduce_grids(g3)
+    assert all(np.array_equal(g3[k].numpy(), grids[k].numpy()) for k in range(3))
     if rank == 0:
         q.put(([g.numpy() for g in grids], int(steps.item())))
     dist.barrier()
