@@ -587,6 +587,34 @@ def run_e2e_grid(a, wl, nsource, world, rank, dev):
                     "grids instead of seven trajectory arrays"}
 
 
+def host_timeline(L, h):
+    """Summary of rwrt_last_host_windows: where the last host-buffer call spent its time."""
+    from rwrt_b200 import lib
+    n = C.c_int(0)
+    buf = (C.c_double * (8 * 256))()
+    if L.rwrt_last_host_windows(h, buf, 256, C.byref(n)) != 0 or n.value == 0:
+        return None
+    rows = np.array(buf[: 8 * min(n.value, 256)]).reshape(-1, 8)
+    link_ms = rows[:, 5] - rows[:, 4]
+    hxw = rows[:, 0] == 0
+    out = {"windows": int(len(rows)), "direct_windows": int((~hxw).sum()),
+           "link_busy_ms": round(float(link_ms.sum()), 1), "link_gbs": round(float(rows[:, 1].sum() / max(link_ms.sum(), 1e-9) / 1e6), 1),
+           "slowest_window_link_gbs": round(float((rows[:, 1] / np.maximum(link_ms, 1e-9) / 1e6).min()), 1),
+           "last_copy_done_ms": round(float(rows[:, 5].max()), 1),
+           "gpu_ready_last_ms": round(float(rows[:, 2].max()), 1)}
+    ph = (C.c_double * 8)()
+    if L.rwrt_last_host_phases(h, ph) == 0:
+        out["phases_ms"] = {"arena": round(ph[0], 1), "inputs_queued": round(ph[1], 1), "pipeline_origin": round(ph[2], 1),
+                            "windows_queued": round(ph[3], 1), "device_done": round(ph[4], 1), "threads_joined": round(ph[5], 1),
+                            "released": round(ph[6], 1), "thread_startup": round(ph[7], 1)}
+    if hxw.any():
+        out["host_expand_ms_per_window_median"] = round(float(np.median(rows[hxw, 7] - rows[hxw, 6])), 2)
+        out["host_expand_ms_per_window_max"] = round(float((rows[hxw, 7] - rows[hxw, 6]).max()), 2)
+        out["wait_for_host_threads_ms_max"] = round(float((rows[hxw, 6] - rows[hxw, 5]).max()), 2)
+        out["last_window_written_ms"] = round(float(rows[hxw, 7].max()), 1)
+    return out
+
+
 def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags, world, dev):
     """Same metric through rwrt_real2d_host: host inputs, pinned host outputs, copies inside the timed region."""
     import torch
@@ -634,11 +662,12 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
     reps = max(1, min(a.steps, 8))
     t0 = time.perf_counter()
     steps = 0
-    per_rep = []
+    per_rep, timelines = [], []
     for _ in range(reps):
         t_rep = time.perf_counter()
         call()                               # synchronises before returning
         per_rep.append(round(1e3 * (time.perf_counter() - t_rep), 1))
+        timelines.append(host_timeline(L, h))
         steps += int(tot_h.item())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
@@ -670,6 +699,9 @@ def run_e2e(a, L, h, wl, slon, slat, nsource, nzwn, nt, N, tstep, ttotal, flags,
     return {"value": float(s.item()) / float(t.item()), "unit": "steps/s", "h2d_bytes_per_step": int(hs[1]),
             "d2h_bytes_per_step": int(hs[0]), "result_bytes_per_step": d2h, "ms_per_step": 1e3 * float(t.item()) / reps,
             "ms_per_call": per_rep,          # this rank's calls (the value is total steps / total time, max over ranks)
+            # where the fastest and the slowest of those calls spent their time (rwrt_last_host_windows: link rate per time
+            # window, host threads' time per window, waits)
+            "timeline_fastest_call": timelines[int(np.argmin(per_rep))], "timeline_slowest_call": timelines[int(np.argmax(per_rep))],
             "link_during_calls": link,
             "api": "rwrt_real2d_host (C ABI, host pointers; pinned inputs and result arrays)", "transfer": how}
 

@@ -251,6 +251,21 @@ int rwrt_last_run_times(rwrt_handle h, double *ms4);
  * were copied straight into the caller's pinned planes */
 int rwrt_last_host_stats(rwrt_handle h, double *stats5);
 
+/* Timeline of the last host-buffer call (rwrt_real2d_host / rwrt_ray_run_rk45_d2h with host-side expansion), one row of
+ * RWRT_HOST_WINDOW_FIELDS doubles per time window, all times in ms since the call's pipeline started (device events and
+ * the host clock share the origin): [0] route (0 packed rows + host threads, 1 direct copy of device-expanded rows),
+ * [1] bytes on the link, [2] device: window ready to travel, [3] host: copy queued, [4] copy could start (link free,
+ * data ready, queued), [5] device: copy finished, [6] host threads: first chunk of the window started (-1: direct),
+ * [7] host threads: window completely in the caller's arrays (-1: direct).  [5]-[4] with [1] gives the link rate of
+ * a window, [7]-[6] the host threads' time on it, [6]-[5] how long it waited for them.  *nwindows = rows available. */
+/* Host-clock ms since entry into the last rwrt_real2d_host at the end of each phase: [0] device arena allocated,
+ * [1] inputs, BS.ready and t = 0 state queued, [2] origin of the window timeline (live rays compacted, t = 0 row on the
+ * host, events created), [3] all windows queued, [4] device work and copies finished, [5] host threads joined,
+ * [6] per-call objects released (= return); [7] ms spent starting the host threads. */
+int rwrt_last_host_phases(rwrt_handle h, double *ms8);
+#define RWRT_HOST_WINDOW_FIELDS 8
+int rwrt_last_host_windows(rwrt_handle h, double *rows, int max_windows, int *nwindows);
+
 /* Roofline denominator: measured FP64 FMA throughput of the device (TFLOP/s, register-resident DFMA
  * chains).  Diagnostic only; used by bench.py next to MEASURED_PEAKS.json, which has no FP64 figure. */
 int rwrt_measure_fp64_peak(rwrt_handle h, double *tflops);

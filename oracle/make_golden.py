@@ -115,7 +115,8 @@ def pointwise_fixture():
     plat = rng.uniform(-1.6, 1.6, n)
     plat[:10] = [np.pi / 2, -np.pi / 2, 0, 1.5533, -1.5533, 1.56, -1.56, 1.5707, 0.3, 0.3]
     plon[:6] = [0, 2 * np.pi, -1e-17, 4 * np.pi, -2 * np.pi, 6.283185307179586]
-    merc = np.asarray(w.bs.cal_bs_mercator_point(plon, plat, mode="numpy"))[:12].T.copy()
+    merc18 = np.asarray(w.bs.cal_bs_mercator_point(plon, plat, mode="numpy")).T.copy()      # all 18 rows (bs.py:884-887)
+    merc = merc18[:, :12].copy()
     # RHS: y = (lon, lat, k, l, A) as (5, n, 1, 1) -> wr.py:492-556
     k = rng.integers(1, 9, n).astype("float64")
     l = rng.uniform(-60, 60, n)
@@ -153,9 +154,29 @@ def pointwise_fixture():
         ky[f"ky_k{int(kz)}_{'s' if fr == 0 else ('p' if fr > 0 else 'n')}"] = np.asarray(ml)
         ky[f"kyarg_k{int(kz)}_{'s' if fr == 0 else ('p' if fr > 0 else 'n')}"] = np.array([kz, fr])
     np.savez_compressed(os.path.join(GOLD, "pointwise.npz"), u_sha=sha(u), v_sha=sha(v), plon=plon, plat=plat,
-                        merc=merc, y=y.T.copy(), dy=dy, polys=np.array(polys), roots=np.array(roots),
+                        merc=merc, merc18=merc18, y=y.T.copy(), dy=dy, polys=np.array(polys), roots=np.array(roots),
                         fu=fu, fv=fv, fqx=fqx, fqy=fqy, **ky)
     print("pointwise.npz written")
+
+
+def ky_frac_fixture():
+    """cal_ky (bs.py:985-1040) with FRACTIONAL zonal wavenumbers: zwn**3 goes through libm pow there (bs.py:1006),
+    so the leading coefficient is only reproduced by a correctly rounded cube (CUDA pow is 2 ulp)."""
+    m = refshim.load()
+    rng = np.random.default_rng(77)
+    n = 2000
+    fu = rng.uniform(-20, 60, n)
+    fv = np.where(rng.uniform(size=n) < 0.1, 0.0, rng.uniform(-3, 3, n))
+    fqx = rng.uniform(-30, 30, n)
+    fqy = rng.uniform(-50, 300, n)
+    out = dict(fu=fu, fv=fv, fqx=fqx, fqy=fqy)
+    for j, (kz, fr) in enumerate(((1.5, 0.0), (2.7, 0.0), (0.8, 0.0), (3.3, 2 * np.pi / (30 * 86400.0)),
+                                  (6.1, -2 * np.pi / (20 * 86400.0)), (1.0 / 3.0, 0.0))):
+        ml, _ = m["bs"].cal_ky(fu, fv, fqx, fqy, np.array([fr]), np.float64(kz), mode="numpy", root_method="numpy")
+        out[f"ky_{j}"] = np.asarray(ml)
+        out[f"kyarg_{j}"] = np.array([kz, fr])
+    np.savez_compressed(os.path.join(GOLD, "ky_frac.npz"), **out)
+    print("ky_frac.npz written")
 
 
 def kat_fixture():
@@ -194,32 +215,93 @@ def kat_fixture():
     np.savez_compressed(os.path.join(GOLD, "kat.npz"), **out)
 
 
+FIXTURES = {}     # name -> zero-argument maker (filled by _register below)
+
+
+def check(names=None, verbose=True):
+    """`python -m oracle.make_golden --check [names]`: regenerate fixtures from the live reference into a scratch
+    directory and compare them with the committed files, array by array, bit for bit.  Returns the list of
+    differing (file, key) pairs (empty = the committed fixtures ARE the reference's outputs)."""
+    import tempfile
+    global GOLD
+    committed = GOLD
+    bad = []
+    with tempfile.TemporaryDirectory() as tmp:
+        GOLD = tmp
+        try:
+            for name in (names or list(FIXTURES)):
+                FIXTURES[name]()
+                new = np.load(os.path.join(tmp, name + ".npz"), allow_pickle=False)
+                old = np.load(os.path.join(committed, name + ".npz"), allow_pickle=False)
+                if sorted(new.files) != sorted(old.files):
+                    bad.append((name, "<key set>"))
+                    continue
+                for k in new.files:
+                    a, b = new[k], old[k]
+                    same = a.shape == b.shape and a.dtype == b.dtype and (
+                        np.array_equal(a, b, equal_nan=True) if a.dtype.kind in "fc" else np.array_equal(a, b))
+                    if not same:
+                        bad.append((name, k))
+                if verbose:
+                    print(f"check {name}: {'OK' if not [x for x in bad if x[0] == name] else 'DIFFERS'} ({len(new.files)} arrays)")
+        finally:
+            GOLD = committed
+    return bad
+
+
+def _register():
+    F = FIXTURES
+    F["fields"] = fields_fixture
+    F["pointwise"] = pointwise_fixture
+    F["ky_frac"] = ky_frac_fixture
+    F["kat"] = kat_fixture
+    # C1: BASELINE.json configs[0] -- single source, k = 1..3, Jet-Z on 2.5 deg, 30 days
+    F["c1_jet"] = lambda: trajectory_fixture("c1_jet", "jet_z", {}, [1.0, 2.0, 3.0], [120.0], [30.0], 30.0)
+    # great-circle known-answer case (manual section 2): solid-body rotation, k = 1..5
+    F["great_circle"] = lambda: trajectory_fixture("great_circle", "great_circle", {}, [1.0, 2.0, 3.0, 4.0, 5.0], [0.0] * 5,
+                                                   [0.0, 5.0, 10.0, 15.0, 20.0], 30.0)
+
+    def clim_g1():   # Clim on 2.5 deg: seeded random sources, k = 1..4, 12 days (cubic roots, zonally varying flow)
+        sl, sa = synthetic.random_sources(16, 7)
+        trajectory_fixture("clim_g1", "clim", dict(nlon=144, nlat=73), [1.0, 2.0, 3.0, 4.0], sl, sa, 12.0)
+
+    def clim_g1_freq():   # non-stationary waves: period 30 days (omega enters the t=0 cubic only, bs.py:1005)
+        sl, sa = synthetic.random_sources(10, 19, max_abs_lat_deg=60.0)
+        trajectory_fixture("clim_g1_freq", "clim", dict(nlon=144, nlat=73), [1.0, 3.0, 5.0], sl, sa, 8.0,
+                           freq=2 * np.pi / (30 * 86400.0))
+
+    def clim_g2():   # 1 degree grid, short
+        sl, sa = synthetic.random_sources(10, 23)
+        trajectory_fixture("clim_g2", "clim", dict(nlon=360, nlat=181), [2.0, 4.0, 6.0], sl, sa, 6.0)
+
+    def rk4_clim_g1():
+        sl, sa = synthetic.random_sources(14, 31)
+        trajectory_fixture("rk4_clim_g1", "clim", dict(nlon=144, nlat=73), [1.0, 2.0, 4.0], sl, sa, 10.0, rk4=True)
+
+    F["clim_g1"], F["clim_g1_freq"], F["clim_g2"] = clim_g1, clim_g1_freq, clim_g2
+    # the fixed-step RK4 path (inte_method='', main_wr.py's default): wr.py:702-765
+    F["rk4_jet"] = lambda: trajectory_fixture("rk4_jet", "jet_z", {}, [1.0, 2.0, 3.0], [120.0, 60.0], [30.0, 20.0], 20.0, rk4=True)
+    F["rk4_clim_g1"] = rk4_clim_g1
+
+
+_register()
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if not refshim.available():
         raise SystemExit("reference not mounted at /root/reference")
-    fields_fixture()
-    pointwise_fixture()
-    kat_fixture()
-    # C1: BASELINE.json configs[0] -- single source, k = 1..3, Jet-Z on 2.5 deg, 30 days
-    trajectory_fixture("c1_jet", "jet_z", {}, [1.0, 2.0, 3.0], [120.0], [30.0], 30.0)
-    # great-circle known-answer case (manual section 2): solid-body rotation, k = 1..5
-    trajectory_fixture("great_circle", "great_circle", {}, [1.0, 2.0, 3.0, 4.0, 5.0], [0.0] * 5,
-                       [0.0, 5.0, 10.0, 15.0, 20.0], 30.0)
-    # Clim on 2.5 deg: seeded random sources, k = 1..4, 12 days (cubic roots, zonally varying flow)
-    sl, sa = synthetic.random_sources(16, 7)
-    trajectory_fixture("clim_g1", "clim", dict(nlon=144, nlat=73), [1.0, 2.0, 3.0, 4.0], sl, sa, 12.0)
-    # non-stationary waves: period 30 days (omega enters the t=0 cubic only, bs.py:1005)
-    sl, sa = synthetic.random_sources(10, 19, max_abs_lat_deg=60.0)
-    trajectory_fixture("clim_g1_freq", "clim", dict(nlon=144, nlat=73), [1.0, 3.0, 5.0], sl, sa, 8.0,
-                       freq=2 * np.pi / (30 * 86400.0))
-    # 1 degree grid, short
-    sl, sa = synthetic.random_sources(10, 23)
-    trajectory_fixture("clim_g2", "clim", dict(nlon=360, nlat=181), [2.0, 4.0, 6.0], sl, sa, 6.0)
-    # the fixed-step RK4 path (inte_method='', main_wr.py's default): wr.py:702-765
-    trajectory_fixture("rk4_jet", "jet_z", {}, [1.0, 2.0, 3.0], [120.0, 60.0], [30.0, 20.0], 20.0, rk4=True)
-    sl, sa = synthetic.random_sources(14, 31)
-    trajectory_fixture("rk4_clim_g1", "clim", dict(nlon=144, nlat=73), [1.0, 2.0, 4.0], sl, sa, 10.0, rk4=True)
+    if "--check" in sys.argv:
+        names = [a for a in sys.argv[sys.argv.index("--check") + 1:] if not a.startswith("-")]
+        bad = check(names or None)
+        if bad:
+            raise SystemExit(f"committed fixtures differ from the live reference: {bad}")
+        print("all checked fixtures are bit-identical to the live reference's outputs")
+        return
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    for name, make in FIXTURES.items():
+        if not only or name in only:
+            make()
 
 
 if __name__ == "__main__":

@@ -5,6 +5,7 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -78,6 +79,27 @@ struct rwrt_ctx {
     bool ready = false;
     double lon0 = 0, dlon = 0, lat0 = 0, dlat = 0;
     DevBuf fpk, scratch, trig, live, state, counters, blockcnt, inv, rows_done, records, packed, direct, row0;
+    DevBuf arena;                      // inputs / counters / t = 0 row of the host-buffer calls; kept between calls: a cudaFree per
+                                       // call stalled for ~0.5 s every few calls (rwrt_last_host_phases showed 280 -> 770 ms)
+    cudaStream_t copy_stream = nullptr;   // D2H stream of the host-buffer calls, created on first use
+    // per-call objects of the host-buffer calls, pooled on the handle (creating ~100 events and faulting in a fresh slot
+    // map in every call showed up as occasional 70 ms stalls before the first window)
+    std::vector<cudaEvent_t> hx_ev_ready, hx_ev_copied;   // per time window
+    cudaEvent_t hx_ev_t0 = nullptr;
+    int32_t *hx_inv = nullptr;            // pinned host copy of the slot -> ray map
+    size_t hx_inv_cap = 0;
+    void release_hx_pools()
+    {
+        for (auto e : hx_ev_ready) cudaEventDestroy(e);
+        for (auto e : hx_ev_copied) cudaEventDestroy(e);
+        hx_ev_ready.clear();
+        hx_ev_copied.clear();
+        if (hx_ev_t0) cudaEventDestroy(hx_ev_t0);
+        hx_ev_t0 = nullptr;
+        if (hx_inv) cudaFreeHost(hx_inv);
+        hx_inv = nullptr;
+        hx_inv_cap = 0;
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> ev_win;   // per time window: start / end of the integrate kernel (timing of the dominant kernel alone)
     int n_win_timed = 0;
@@ -91,6 +113,8 @@ struct rwrt_ctx {
     void *hx_stage[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t hx_stage_cap = 0;
     int hx_nstage = 0;
+    double host_phases[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last rwrt_real2d_host: host-clock ms at the end of each phase (rwrt_last_host_phases)
+    std::vector<double> host_windows;        // last host-buffer call: RWRT_HOST_WINDOW_FIELDS doubles per time window (rwrt_last_host_windows)
     double host_stats[5] = {0, 0, 0, 0, 0};  // last host-buffer call: bytes D2H, bytes H2D, time windows, host threads, direct windows
     void release_hx_staging()
     {
@@ -377,6 +401,9 @@ int rwrt_destroy(rwrt_handle h)
     h->packed.release();
     h->direct.release();
     h->row0.release();
+    h->arena.release();
+    h->release_hx_pools();
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto e : h->ev_win) cudaEventDestroy(e);
     h->ev_win.clear();
     h->scratch.release();
@@ -528,7 +555,7 @@ struct HostExpand {
     // filled by hx_begin
     long long nlive = 0;
     int rec_rows = 0, nwin = 0;
-    std::vector<int32_t> inv;               // slot -> live index (host copy)
+    const int32_t *inv = nullptr;           // slot -> live index (pinned host copy, owned by the handle)
     double *stage[HX_STAGES] = {};          // pinned (owned by the handle): packed rows of one window, 7 x rows x nlive doubles
     std::vector<cudaEvent_t> packed_ev, copied;     // per window
     std::vector<int> w_begin, w_end;
@@ -543,6 +570,13 @@ struct HostExpand {
     std::vector<std::thread> workers;
     std::atomic<int> next_task{0};
     std::atomic<bool> abort{false};
+    // timeline of the call (rwrt_last_host_windows): one clock origin for the device events and the host clock
+    cudaEvent_t ev_t0 = nullptr;
+    std::chrono::steady_clock::time_point t0;
+    std::vector<double> bytes_w, t_enqueued;                 // per window: bytes on the link; host ms when its copy was queued
+    std::vector<std::atomic<long long>> *t_first = nullptr;  // per window: host ns of the first / last chunk written by the threads
+    std::vector<std::atomic<long long>> *t_last = nullptr;
+    rwrt_handle owner = nullptr;
     std::mutex mu;                          // waits (window queued / window expanded) sleep on cv instead of spinning:
     std::condition_variable cv;             // the launching thread and the CUDA driver threads need the cores too
 };
@@ -872,16 +906,23 @@ static void hx_worker(HostExpand *hx, int device)
         }
         const long long s0 = (long long)c * hx->chunk_slots;
         const long long s1 = s0 + hx->chunk_slots < hx->N ? s0 + hx->chunk_slots : hx->N;
+        {
+            const long long now = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - hx->t0).count();
+            long long cur = (*hx->t_first)[w].load(std::memory_order_relaxed);
+            while ((cur < 0 || now < cur) && !(*hx->t_first)[w].compare_exchange_weak(cur, now, std::memory_order_relaxed)) {}
+        }
         HxView v;
         v.out = hx->out7_host;
         v.pl = (size_t)hx->nt * hx->N;
         v.N = hx->N;
-        v.inv = hx->inv.data();
+        v.inv = hx->inv;
         v.packed = hx->stage[hx->stage_of[w]];
         v.nray = hx->nlive;
         v.rows = hx->w_end[w] - hx->w_begin[w];
         hx_expand_rows(v, hx->w_begin[w], s0, s1);
         if ((*hx->chunks_done)[w].fetch_add(1, std::memory_order_acq_rel) + 1 == hx->nchunk) {   // window w is in the caller's arrays
+            (*hx->t_last)[w].store(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - hx->t0).count(),
+                                   std::memory_order_relaxed);
             std::lock_guard<std::mutex> lk(hx->mu);
             hx->hx_finished.fetch_add(1, std::memory_order_release);
             hx->cv.notify_all();
@@ -895,8 +936,18 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_
     hx->nlive = nlive;
     hx->rec_rows = rec_rows;
     hx->nwin = nwin;
-    hx->inv.resize((size_t)hx->N);
-    CU(cudaMemcpyAsync(hx->inv.data(), h->inv.p, (size_t)hx->N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (h->hx_inv_cap < (size_t)hx->N) {
+        if (h->hx_inv) cudaFreeHost(h->hx_inv);
+        h->hx_inv = nullptr;
+        h->hx_inv_cap = 0;
+        if (cudaMallocHost((void **)&h->hx_inv, (size_t)hx->N * sizeof(int32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(RWRT_ERR_NOMEM, "pinned slot map (%lld slots)", hx->N);
+        }
+        h->hx_inv_cap = (size_t)hx->N;
+    }
+    hx->inv = h->hx_inv;
+    CU(cudaMemcpyAsync(h->hx_inv, h->inv.p, (size_t)hx->N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     // row 0 (the t = 0 state, wr.py:768-781) goes to the caller's planes now: the workers read the constant values of
     // NaN-root slots from it
     CU(cudaMemcpy2DAsync(hx->out7_host, (size_t)hx->nt * hx->N * sizeof(double), out7_dev, dev_pl * sizeof(double),
@@ -925,12 +976,30 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_
     hx->route.assign(nwin, 0);
     hx->stage_of.assign(nwin, 0);
     hx->hx_windows.clear();
+    while ((int)h->hx_ev_ready.size() < nwin) {    // timing enabled: the per-window timeline of rwrt_last_host_windows
+        cudaEvent_t a = nullptr, b = nullptr;
+        CU(cudaEventCreate(&a));
+        h->hx_ev_ready.push_back(a);
+        CU(cudaEventCreateWithFlags(&b, cudaEventBlockingSync));
+        h->hx_ev_copied.push_back(b);
+    }
     for (int w = 0; w < nwin; ++w) {
-        CU(cudaEventCreateWithFlags(&hx->packed_ev[w], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&hx->copied[w], cudaEventDisableTiming | cudaEventBlockingSync));
+        hx->packed_ev[w] = h->hx_ev_ready[w];
+        hx->copied[w] = h->hx_ev_copied[w];
     }
     hx->chunks_done = new std::vector<std::atomic<int>>(nwin);
     for (auto &a : *hx->chunks_done) a.store(0);
+    hx->t_first = new std::vector<std::atomic<long long>>(nwin);
+    hx->t_last = new std::vector<std::atomic<long long>>(nwin);
+    for (auto &a : *hx->t_first) a.store(-1);
+    for (auto &a : *hx->t_last) a.store(-1);
+    hx->bytes_w.assign(nwin, 0.0);
+    hx->t_enqueued.assign(nwin, 0.0);
+    hx->owner = h;
+    if (!h->hx_ev_t0) CU(cudaEventCreate(&h->hx_ev_t0));
+    hx->ev_t0 = h->hx_ev_t0;
+    CU(cudaEventRecord(hx->ev_t0, s));           // the stream is idle here (synchronised above): device and host clocks start together
+    hx->t0 = std::chrono::steady_clock::now();
     hx->chunk_slots = HX_CHUNK;                 // multiple of 8: 64-byte lines stay whole when N is a multiple of 8
     hx->nchunk = (int)((hx->N + hx->chunk_slots - 1) / hx->chunk_slots);
     // worker threads: the cores this process may run on, shared between the ranks of a multi-GPU launch
@@ -942,7 +1011,9 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_
         // ranks share the host's memory bandwidth: two thirds of a rank's cores write as fast as all of them and
         // leave room for the launching and driver threads (2 ranks on 24 cores: 8 threads 686 ms per C2 pass, 12: 766)
         if (ranks > 1) nthreads = (2 * nthreads / ranks + 2) / 3;
+        else if (nthreads > 3) nthreads -= 2;
     }
+    else if (nthreads > 3) nthreads -= 2;                   // one rank: leave two cores to the launching thread and the CUDA driver's threads
     if (nthreads > 32) nthreads = 32;                       // the expansion is bound by memory bandwidth long before
     if (const char *e = getenv("RWRT_HOST_THREADS")) nthreads = atoi(e);
     if (nthreads < 1) nthreads = 1;
@@ -953,6 +1024,7 @@ static int hx_begin(HostExpand *hx, rwrt_handle h, const double *out7_dev, size_
         if (hx->workers.empty()) return fail(RWRT_ERR_NOMEM, "could not start a host thread for the result expansion");
         nthreads = (int)hx->workers.size();
     }
+    h->host_phases[7] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hx->t0).count();  // thread start-up
     h->host_stats[0] += (double)hx->N * (sizeof(int32_t) + 7 * sizeof(double));   // slot map + the t = 0 row; windows add theirs
     h->host_stats[2] = nwin;
     h->host_stats[3] = nthreads;
@@ -1031,6 +1103,8 @@ static int hx_on_window(HostExpand *hx, rwrt_handle h, int w, const RunParams &p
         h->host_stats[4] += 1;
     }
     CU(cudaEventRecord(hx->copied[w], hx->copy_stream));
+    hx->bytes_w[w] = (double)bytes;
+    hx->t_enqueued[w] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hx->t0).count();
     h->host_stats[0] += (double)bytes;
     {
         std::lock_guard<std::mutex> lk(hx->mu);
@@ -1050,8 +1124,36 @@ static int hx_finish(HostExpand *hx, bool ok)
     hx->cv.notify_all();
     for (auto &t : hx->workers) t.join();
     hx->workers.clear();
-    for (auto e : hx->packed_ev) if (e) cudaEventDestroy(e);
-    for (auto e : hx->copied) if (e) cudaEventDestroy(e);
+    // timeline of the call, one row per window (all events have completed: the caller synchronised both streams)
+    if (ok && hx->owner && hx->ev_t0 && !hx->abort.load()) {
+        std::vector<double> &tl = hx->owner->host_windows;
+        tl.assign((size_t)hx->nwin * RWRT_HOST_WINDOW_FIELDS, 0.0);
+        float prev_end = 0;
+        for (int w = 0; w < hx->nwin; ++w) {
+            float t_ready = 0, t_end = 0;
+            if (cudaEventElapsedTime(&t_ready, hx->ev_t0, hx->packed_ev[w]) != cudaSuccess ||
+                cudaEventElapsedTime(&t_end, hx->ev_t0, hx->copied[w]) != cudaSuccess) {
+                cudaGetLastError();
+                tl.clear();
+                break;
+            }
+            double *r = tl.data() + (size_t)w * RWRT_HOST_WINDOW_FIELDS;
+            r[0] = hx->route[w];
+            r[1] = hx->bytes_w[w];
+            r[2] = t_ready;                                      // device: rows of the window ready to travel
+            r[3] = hx->t_enqueued[w];                            // host: copy queued (after the routing decision)
+            r[4] = t_ready > prev_end ? t_ready : prev_end;      // device: the link is free and the data ready (copies are serial) ...
+            if (r[3] > r[4]) r[4] = r[3];                        // ... and the copy has been queued
+            r[5] = t_end;                                        // device: copy finished
+            r[6] = (*hx->t_first)[w].load() < 0 ? -1.0 : (*hx->t_first)[w].load() * 1e-6;   // host threads: first chunk started
+            r[7] = (*hx->t_last)[w].load() < 0 ? -1.0 : (*hx->t_last)[w].load() * 1e-6;     // ... last chunk written
+            prev_end = t_end;
+        }
+    }
+    hx->ev_t0 = nullptr;                    // the events belong to the handle's pools
+    delete hx->t_first;
+    delete hx->t_last;
+    hx->t_first = hx->t_last = nullptr;
     hx->packed_ev.clear();
     hx->copied.clear();
     delete hx->chunks_done;
@@ -1103,6 +1205,8 @@ int rwrt_trim(rwrt_handle h)
     h->packed.release();
     h->direct.release();
     h->row0.release();
+    h->arena.release();
+    h->release_hx_pools();
     h->have_records = false;
     h->rows_done.release();
     h->inv.release();
@@ -1155,6 +1259,23 @@ int rwrt_last_host_stats(rwrt_handle h, double *stats5)
 {
     if (!h || !stats5) return fail(RWRT_ERR_ARG, "rwrt_last_host_stats: NULL argument");
     for (int i = 0; i < 5; ++i) stats5[i] = h->host_stats[i];
+    return RWRT_OK;
+}
+
+int rwrt_last_host_phases(rwrt_handle h, double *ms8)
+{
+    if (!h || !ms8) return fail(RWRT_ERR_ARG, "rwrt_last_host_phases: NULL argument");
+    for (int i = 0; i < 8; ++i) ms8[i] = h->host_phases[i];
+    return RWRT_OK;
+}
+
+int rwrt_last_host_windows(rwrt_handle h, double *rows, int max_windows, int *nwindows)
+{
+    if (!h || !nwindows || (max_windows > 0 && !rows)) return fail(RWRT_ERR_ARG, "rwrt_last_host_windows: NULL argument");
+    const int n = (int)(h->host_windows.size() / RWRT_HOST_WINDOW_FIELDS);
+    *nwindows = n;
+    const int m = n < max_windows ? n : max_windows;
+    if (m > 0) memcpy(rows, h->host_windows.data(), (size_t)m * RWRT_HOST_WINDOW_FIELDS * sizeof(double));
     return RWRT_OK;
 }
 
@@ -1392,6 +1513,7 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
 {
     if (!h || !out7_host) return fail(RWRT_ERR_ARG, "rwrt_ray_run_rk45_d2h: NULL argument");
     for (double &x : h->host_stats) x = 0;
+    h->host_windows.clear();
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaSetDevice(h->device));
     const long long N = 3LL * nsource * nzwn;
@@ -1400,8 +1522,8 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
     if (const char *e = getenv("RWRT_HOST_WINDOWS")) nwin = atoi(e);
     if (nwin < 1) nwin = 1;
     if (nwin > 64) nwin = 64;
-    cudaStream_t copy_stream = nullptr;
-    CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    if (!h->copy_stream) CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t copy_stream = h->copy_stream;
     // Default: the device planes are filled as in rwrt_ray_run_rk45 and, beside them, the packed rows of the live rays
     // travel to the host where threads write out7_host (see rwrt_real2d_host); RWRT_HOST_EXPAND=0 or a run without
     // ray records: the finished rows of the device planes are copied as they are.
@@ -1455,7 +1577,6 @@ int rwrt_ray_run_rk45_d2h(rwrt_handle h, int nsource, const int32_t *src_member,
         cudaEventDestroy(ctx.ev[0]);
         cudaEventDestroy(ctx.ev[1]);
     }
-    cudaStreamDestroy(copy_stream);
     return rc;
 }
 
@@ -1467,6 +1588,9 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
                             int64_t *total_accepted_host, void *stream, bool use_hx)
 {
     cudaStream_t s = (cudaStream_t)stream;
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto phase = [&](int i) { h->host_phases[i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(); };
+    for (double &x : h->host_phases) x = 0;
     CU(cudaSetDevice(h->device));
     const size_t ng = (size_t)h->nmember * h->nlon * h->nlat;
     const long long N = 3LL * nsource * nzwn;
@@ -1489,14 +1613,16 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
     size_t o_slon = carve((size_t)nsource * 8), o_slat = carve((size_t)nsource * 8), o_mem = carve((size_t)nsource * 4);
     size_t o_zwn = carve((size_t)nzwn * 8), o_acc = carve((size_t)N * 8), o_st = carve((size_t)N), o_tot = carve(8);
     size_t o_out = carve(use_hx ? (size_t)7 * N * 8 : nout * 8);
-    char *arena = nullptr;
-    CU(cudaMalloc((void **)&arena, off));
+    if (h->arena.reserve(off)) return fail(RWRT_ERR_NOMEM, "device arena of the host-buffer call (%zu bytes)", off);
+    char *arena = (char *)h->arena.p;
+    phase(0);                                       // device arena allocated
     h->host_stats[0] = (use_hx ? 0.0 : (double)nout * 8) + (accepted_host ? (double)N * 8 : 0.0) + (status_host ? (double)N : 0.0) + 8;
     h->host_stats[1] = (double)ng * 8 + (double)h->nlon * 8 + (double)h->nlat * ((coslat && sinlat) ? 24 : 8) +
                        (double)nsource * (src_member ? 20 : 16) + (double)nzwn * 8;
     h->host_stats[2] = nwin;
     h->host_stats[3] = 0;
     h->host_stats[4] = 0;
+    h->host_windows.clear();
     HostCopyCtx ctx;
     ctx.copy_stream = nullptr;
     ctx.ev[0] = ctx.ev[1] = nullptr;
@@ -1519,7 +1645,8 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
             goto done;                                                                                  \
         }                                                                                               \
     } while (0)
-    CUX(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
+    if (!h->copy_stream) CUX(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    ctx.copy_stream = h->copy_stream;
     hx.copy_stream = ctx.copy_stream;
     hx_configure(&hx);
     CUX(cudaEventCreateWithFlags(&ctx.ev[0], cudaEventDisableTiming));
@@ -1552,6 +1679,7 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
         rc = rwrt_ray_init(h, nsource, (const double *)(arena + o_slon), (const double *)(arena + o_slat), dmem, nzwn,
                            (const double *)(arena + o_zwn), freq, use_hx ? 1 : nt, (double *)(arena + o_out), s);
         if (rc) goto done;
+        phase(1);                                   // inputs, BS.ready and the t = 0 state queued
         RunOpts o;
         o.nwin = nwin;
         o.hook = use_hx ? nullptr : host_copy_hook;
@@ -1561,6 +1689,8 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
                       (double *)(arena + o_out), (int64_t *)(arena + o_acc), nullptr, (int8_t *)(arena + o_st),
                       (int64_t *)(arena + o_tot), s, o);
         if (rc) goto done;      // RWRT_HX_UNSUPPORTED included: the caller runs the device-side expansion instead
+        if (use_hx) h->host_phases[2] = std::chrono::duration<double, std::milli>(hx.t0 - t_entry).count();   // pipeline origin (hx_begin): live rays known, t = 0 row on the host
+        phase(3);                                   // every time window queued (the routing decisions wait for copies: most of the pipeline is over)
     }
     if (!use_hx && ctx.first && nout > 0)  // nothing was integrated (no live ray / nt == 1): plain copy of what there is
         CUX(cudaMemcpyAsync(out7_host, arena + o_out, nout * 8, cudaMemcpyDeviceToHost, s));
@@ -1569,18 +1699,17 @@ static int real2d_host_impl(rwrt_handle h, const float *u, const float *v, const
     if (total_accepted_host) CUX(cudaMemcpyAsync(total_accepted_host, arena + o_tot, 8, cudaMemcpyDeviceToHost, s));
     CUX(cudaStreamSynchronize(s));
     CUX(cudaStreamSynchronize(ctx.copy_stream));
+    phase(4);                                       // device work and copies finished
 done:
     if (use_hx) {
         int rc2 = hx_finish(&hx, rc == RWRT_OK);    // joins the workers: every window is in the caller's arrays
         if (rc == RWRT_OK && rc2) rc = fail(rc2, "host-side expansion failed");
     }
-    if (ctx.copy_stream) {
-        cudaStreamSynchronize(ctx.copy_stream);
-        cudaStreamDestroy(ctx.copy_stream);
-    }
+    phase(5);                                       // host threads joined
+    if (ctx.copy_stream) cudaStreamSynchronize(ctx.copy_stream);
     if (ctx.ev[0]) cudaEventDestroy(ctx.ev[0]);
     if (ctx.ev[1]) cudaEventDestroy(ctx.ev[1]);
-    cudaFree(arena);
+    phase(6);                                       // per-call objects released
     return rc;
 #undef CUX
 }

@@ -349,6 +349,17 @@ __device__ void change_roots_order(double *mwn, int deg)
     t = mwn[0]; mwn[0] = mwn[2]; mwn[2] = t;  // return mwn[::-1]
 }
 
+// k^3 rounded once.  The reference evaluates zwn**3 through libm pow (bs.py:1006), which is correctly rounded in all
+// but the rarest cases (< 0.52 ulp); CUDA's pow() is specified to 2 ulp, which for a fractional zonal wavenumber could
+// move the leading cubic coefficient by an ulp and with it near-degenerate roots across the |Im| < 1e-8 filter.
+// Exact product in double-double (error-free transformations through fma), one final rounding.
+__device__ __forceinline__ double cube_rn(double k)
+{
+    const double hi = k * k, lo = fma(k, k, -hi);       // k^2 = hi + lo exactly
+    const double qh = hi * k, ql = fma(hi, k, -qh);     // hi k = qh + ql exactly
+    return qh + fma(lo, k, ql);
+}
+
 // bs.py:985-1040 for one (source, k)
 __device__ void cal_ky_point(double fu, double fv, double fqx, double fqy, double freq, double k, double *l)
 {
@@ -356,7 +367,7 @@ __device__ void cal_ky_point(double fu, double fv, double fqx, double fqy, doubl
     if (k == 0) return;
     double ps = freq / k * REARTH;
     double coeff[4];
-    coeff[0] = pow(k, 3.0) * (fu - ps - (fqy / (k * k)));
+    coeff[0] = cube_rn(k) * (fu - ps - (fqy / (k * k)));
     coeff[1] = (k * k) * fv + fqx;
     coeff[2] = k * (fu - ps);
     coeff[3] = fv;

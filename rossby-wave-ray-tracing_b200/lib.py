@@ -23,7 +23,7 @@ SYMBOLS = (
     "rwrt_create", "rwrt_destroy", "rwrt_trim", "rwrt_bs_ready", "rwrt_bs_set_fields", "rwrt_sample_mercator", "rwrt_sample_mercator18", "rwrt_rhs",
     "rwrt_ray_init", "rwrt_ray_run_rk45", "rwrt_ray_run_rk45_d2h", "rwrt_ray_run_rk4", "rwrt_grid_accumulate", "rwrt_real2d_host", "rwrt_host_expand_rows", "rwrt_last_host_stats", "rwrt_last_run_stats", "rwrt_measure_fp64_peak",
     "rwrt_ray_sweep_grid", "rwrt_ray_run_rk45_records", "rwrt_records_info", "rwrt_records_expand",
-    "rwrt_grid_accumulate_records", "rwrt_last_run_times",
+    "rwrt_grid_accumulate_records", "rwrt_last_run_times", "rwrt_last_host_windows", "rwrt_last_host_phases",
     "rwrt_shsf_plan_create", "rwrt_shsf_out_shape", "rwrt_shsf_apply", "rwrt_shsf_plan_destroy",
 )
 
@@ -71,6 +71,8 @@ def load():
     L.rwrt_records_expand.argtypes = [vp, i32, i32, vp, vp]
     L.rwrt_grid_accumulate_records.argtypes = [vp, f64, f64, i32, i32, vp, vp, vp, vp]
     L.rwrt_last_run_times.argtypes = [vp, C.POINTER(f64)]
+    L.rwrt_last_host_phases.argtypes = [vp, C.POINTER(f64)]
+    L.rwrt_last_host_windows.argtypes = [vp, C.POINTER(f64), i32, C.POINTER(i32)]
     L.rwrt_real2d_host.argtypes = ([vp] + [vp] * 6 + [i32, vp, vp, vp, i32, vp, f64, i32] + [f64] * 6 +
                                    [u32, vp, vp, vp, vp, vp])
     L.rwrt_host_expand_rows.argtypes = [vp, i32, i64, vp, vp, i64, i32, i32, i64, i64]

@@ -109,3 +109,17 @@ def oracle_nongrazing(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, ref=None, a
             ng &= np.degrees(np.where(np.isnan(d), 0.0, d).max(axis=0)) < 1e-7
         ng &= acc == acc_p
     return ref, acc, ng
+
+
+def record(label, stats):
+    """Append one comparison's statistics (incl. `grazing_within_tol`: how many of the rays the reference itself is
+    chaotic on agree anyway) to the parity table of this run: $RWRT_PARITY_OUT or gpurun_out/parity_table.jsonl.
+    profiles/r2_parity_table.md is that file from the round's GPU run, tabulated (tools/parity_table.py)."""
+    import json
+    path = os.environ.get("RWRT_PARITY_OUT") or os.path.join(os.path.dirname(GOLD[:-len("/golden")]), "gpurun_out", "parity_table.jsonl")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "a") as f:
+            f.write(json.dumps({"case": label, **stats}) + "\n")
+    except OSError:
+        pass

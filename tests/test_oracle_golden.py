@@ -110,6 +110,16 @@ def test_cal_ky_slot_order():
         assert np.array_equal(got, g[key], equal_nan=True), key
 
 
+def test_cal_ky_fractional_wavenumbers():
+    """bs.py:1006: zwn**3 through libm pow -- fractional k; slot layout and values bit for bit."""
+    g = parity.load("ky_frac")
+    for key in [k for k in g.files if k.startswith("ky_")]:
+        kz, fr = g["kyarg_" + key[3:]]
+        got = oracle.cal_ky(g["fu"], g["fv"], g["fqx"], g["fqy"], fr, kz)
+        assert np.array_equal(got, g[key], equal_nan=True), key
+        assert np.isfinite(g[key]).sum() > 500
+
+
 @pytest.mark.parametrize("tag", ["lorenz", "lorenz_loose", "poly", "expo"])
 def test_solver_known_answers(tag):
     """rkf45.py:772-882 demo ODEs through the reference's RK45 class vs the oracle's controller."""

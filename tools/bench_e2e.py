@@ -49,15 +49,18 @@ def main():
         for k, v in env.items():
             os.environ[k] = v
         call()      # warm-up: staging buffers of this setting
-        ts = []
+        ts, tls = [], []
         for _ in range(int(os.environ.get("RWRT_BENCH_CALLS", "4"))):
             t0 = time.perf_counter()
             call()
             ts.append(1e3 * (time.perf_counter() - t0))
+            tls.append(bench.host_timeline(L, h))
         hs = (C.c_double * 5)()
         L.rwrt_last_host_stats(h, hs)
         print(f"{setting or 'default':50s} ms/pass min {min(ts):7.1f} median {sorted(ts)[len(ts)//2]:7.1f} all {[round(t) for t in ts]}   "
               f"d2h {hs[0]/1e9:.2f} GB, {int(hs[2])} windows ({int(hs[4])} direct), {int(hs[3])} threads, steps {int(tot_h.item())}", flush=True)
+        print("     fastest call:", tls[int(np.argmin(ts))], flush=True)
+        print("     slowest call:", tls[int(np.argmax(ts))], flush=True)
         for k in env:
             del os.environ[k]
     L.rwrt_destroy(h)
