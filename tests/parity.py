@@ -94,7 +94,10 @@ def oracle_run(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, tstep_h=2.0):
 
 def oracle_nongrazing(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, ref=None, acc=None):
     """Non-grazing mask from the oracle itself: the base run and four runs with the sources moved by
-    +-1 ulp in longitude / latitude must agree to < 1e-7 deg, in NaN pattern and in step counts."""
+    +-1 ulp in longitude / latitude must agree to < 1e-7 deg, in NaN pattern and in step counts -- and, so that the
+    auxiliary bar on the other state components (relative 1e-5 on k, l, A, u_g, v_g in `compare`) is asserted only
+    where the oracle itself is insensitive, to 1e-6 relative in those components (over 60 days a ray can keep its
+    position to 1e-7 deg while k or l next to a critical line already differ by 1e-4 between two oracle runs)."""
     if ref is None:
         ref, acc = oracle_run(u, v, slon_rad, slat_rad, zwn, days, freq)
     ng = np.ones(acc.shape, dtype=bool)
@@ -107,6 +110,10 @@ def oracle_nongrazing(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, ref=None, a
             with np.errstate(invalid="ignore"):
                 d = np.abs(ref[n] - per[n])
             ng &= np.degrees(np.where(np.isnan(d), 0.0, d).max(axis=0)) < 1e-7
+        for n in ("rzwn", "rmwn", "ramp", "rug", "rvg"):
+            with np.errstate(invalid="ignore", divide="ignore"):
+                rel = np.abs(ref[n] - per[n]) / np.maximum(np.abs(ref[n]), 1e-3)
+            ng &= np.where(np.isnan(rel), 0.0, rel).max(axis=0) < 1e-6
         ng &= acc == acc_p
     return ref, acc, ng
 
