@@ -740,7 +740,8 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         int v = atoi(e);
         if (v >= 1 && v < per_sm) per_sm = v;
     }
-    long long want = ((long long)nlive + 127) / 128;
+    const int bt = strict ? threads_rk45_strict(coop) : threads_rk45_fast(coop);   // threads per block of the integrator
+    long long want = ((long long)nlive + bt - 1) / bt;
     int integrate_blocks = (int)(want < (long long)per_sm * h->sm_count ? want : (long long)per_sm * h->sm_count);
     if (integrate_blocks < 1) integrate_blocks = 1;
     int prepare_blocks = (int)(((long long)nlive + 127) / 128);

@@ -19,6 +19,8 @@ void launch_expand_records_strict(const RunParams &p, cudaStream_t s);
 void launch_rk4_fast(const RunParams &p, cudaStream_t s);
 void launch_rk4_strict(const RunParams &p, cudaStream_t s);
 int occupancy_rk45_fast(bool coop);
+int threads_rk45_fast(bool coop);
+int threads_rk45_strict(bool coop);
 int occupancy_rk45_strict(bool coop);
 void launch_rhs_fast(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s);
 void launch_rhs_strict(const Grid &g, long long n, const double *y, const int32_t *member, double *dy, cudaStream_t s);

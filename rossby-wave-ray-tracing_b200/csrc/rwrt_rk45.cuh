@@ -532,15 +532,19 @@ constexpr int CO_LIST_OFS = 384, CO_LIST_STRIDE = CO_REC_STRIDE;           // fe
 #define RWRT_TMEM_KS 1
 #endif
 constexpr int CO_TMEM_COLS = 64;     // power of two >= 50
+#ifndef RWRT_CO_THREADS
+#define RWRT_CO_THREADS 128          // threads per block of rk45_integrate_coop (a multiple of 32, <= 128: one TMEM lane per thread)
+#endif
+constexpr int CO_THREADS = RWRT_CO_THREADS;
 #ifndef RWRT_CO_BLOCKS
 #define RWRT_CO_BLOCKS 3
 #endif
 #if RWRT_TMEM_KS
 constexpr int CO_BLOCKS_PER_SM = RWRT_CO_BLOCKS;
-constexpr int CO_SMEM_BYTES = (RK_THREADS / 32) * CO_STAGE_BYTES + 16;
+constexpr int CO_SMEM_BYTES = (CO_THREADS / 32) * CO_STAGE_BYTES + 16;
 #else
 constexpr int CO_BLOCKS_PER_SM = 3;
-constexpr int CO_SMEM_BYTES = (RK_THREADS / 32) * CO_STAGE_BYTES + 5 * 5 * RK_THREADS * (int)sizeof(double);
+constexpr int CO_SMEM_BYTES = (CO_THREADS / 32) * CO_STAGE_BYTES + 5 * 5 * CO_THREADS * (int)sizeof(double);
 #endif
 
 // one stage vector (5 doubles = 10 columns) TMEM -> registers; the values may be used after tm_wait_ld(v)
@@ -660,8 +664,13 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src, u
 // OUT: what happens to an output row -- OUT_ROWS (stored: record or planes; the product path of rwrt_ray_run_rk45),
 // OUT_GRID (added to the ray-density / flux grids: rwrt_ray_sweep_grid, no trajectory is materialised at all), or both.
 // Separate instantiations: the grid arithmetic (two fp64 divisions per output row) stays out of the plain kernel.
+#ifdef RWRT_CO_MAXREG   /* occupancy experiments: an explicit register cap instead of the one launch bounds derive */
+#define RWRT_CO_BOUNDS __maxnreg__(RWRT_CO_MAXREG)
+#else
+#define RWRT_CO_BOUNDS __launch_bounds__(CO_THREADS, CO_BLOCKS_PER_SM)
+#endif
 template <int OUT>
-__global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_coop(RunParams p)
+__global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned FULL = 0xffffffffu;
@@ -671,7 +680,7 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     const unsigned stage_u32 = (unsigned)__cvta_generic_to_shared(stage);
 #if RWRT_TMEM_KS
     // tensor-memory scratch for K2..K6: warp 0 allocates 64 columns, every warp addresses its own 32 lanes
-    unsigned *tm_slot = reinterpret_cast<unsigned *>(smem_raw + (RK_THREADS / 32) * CO_STAGE_BYTES);
+    unsigned *tm_slot = reinterpret_cast<unsigned *>(smem_raw + (CO_THREADS / 32) * CO_STAGE_BYTES);
     if (warp_id == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
                          (unsigned)__cvta_generic_to_shared(tm_slot)),
@@ -685,8 +694,8 @@ __global__ void __launch_bounds__(RK_THREADS, CO_BLOCKS_PER_SM) rk45_integrate_c
     const unsigned tm_base = *tm_slot;
     const unsigned tk = tm_base + ((unsigned)(warp_id * 32) << 16);       // + 10 * (s - 1): K_{s+1}, s = 1..5
 #else
-    double *ks = reinterpret_cast<double *>(smem_raw + (RK_THREADS / 32) * CO_STAGE_BYTES);
-#define KS(s, c) ks[(((s) - 1) * 5 + (c)) * RK_THREADS + tid]            /* K2..K6 <-> s = 1..5 */
+    double *ks = reinterpret_cast<double *>(smem_raw + (CO_THREADS / 32) * CO_STAGE_BYTES);
+#define KS(s, c) ks[(((s) - 1) * 5 + (c)) * CO_THREADS + tid]            /* K2..K6 <-> s = 1..5 */
 #endif
     Lane L;
     L.slot = -1;

@@ -27,11 +27,11 @@ void launch_rk45_window_fast(const RunParams &p, int integrate_blocks, cudaStrea
     if (p.coop) {
         const bool grid = p.g_count != nullptr;
         if (p.no_rows && grid)
-            fast::rk45_integrate_coop<OUT_GRID><<<integrate_blocks, fast::RK_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
+            fast::rk45_integrate_coop<OUT_GRID><<<integrate_blocks, fast::CO_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
         else if (grid)
-            fast::rk45_integrate_coop<OUT_ROWS | OUT_GRID><<<integrate_blocks, fast::RK_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
+            fast::rk45_integrate_coop<OUT_ROWS | OUT_GRID><<<integrate_blocks, fast::CO_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
         else
-            fast::rk45_integrate_coop<OUT_ROWS><<<integrate_blocks, fast::RK_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
+            fast::rk45_integrate_coop<OUT_ROWS><<<integrate_blocks, fast::CO_THREADS, fast::CO_SMEM_BYTES, s>>>(p);
     } else
         fast::rk45_integrate<<<integrate_blocks, fast::RK_THREADS, fast::RK_SMEM_BYTES, s>>>(p);
 }
@@ -46,6 +46,7 @@ void launch_rk4_fast(const RunParams &p, cudaStream_t s)
     }
 }
 
+int threads_rk45_fast(bool coop) { return coop ? fast::CO_THREADS : fast::RK_THREADS; }
 int occupancy_rk45_fast(bool coop)
 {
     int nb = 0;
@@ -53,7 +54,7 @@ int occupancy_rk45_fast(bool coop)
         cudaFuncSetAttribute(fast::rk45_integrate_coop<OUT_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::CO_SMEM_BYTES);
         cudaFuncSetAttribute(fast::rk45_integrate_coop<OUT_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::CO_SMEM_BYTES);
         cudaFuncSetAttribute(fast::rk45_integrate_coop<OUT_ROWS | OUT_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::CO_SMEM_BYTES);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast::rk45_integrate_coop<OUT_ROWS>, fast::RK_THREADS, fast::CO_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast::rk45_integrate_coop<OUT_ROWS>, fast::CO_THREADS, fast::CO_SMEM_BYTES);
 #if RWRT_TMEM_KS
         // the occupancy calculator answers 1 for a kernel that allocates tensor memory (it cannot know how many
         // columns tcgen05.alloc will ask for); this build takes 64 of the 512 columns per block

@@ -27,11 +27,11 @@ void launch_rk45_window_strict(const RunParams &p, int integrate_blocks, cudaStr
     if (p.coop) {
         const bool grid = p.g_count != nullptr;
         if (p.no_rows && grid)
-            strict::rk45_integrate_coop<OUT_GRID><<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
+            strict::rk45_integrate_coop<OUT_GRID><<<integrate_blocks, strict::CO_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
         else if (grid)
-            strict::rk45_integrate_coop<OUT_ROWS | OUT_GRID><<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
+            strict::rk45_integrate_coop<OUT_ROWS | OUT_GRID><<<integrate_blocks, strict::CO_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
         else
-            strict::rk45_integrate_coop<OUT_ROWS><<<integrate_blocks, strict::RK_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
+            strict::rk45_integrate_coop<OUT_ROWS><<<integrate_blocks, strict::CO_THREADS, strict::CO_SMEM_BYTES, s>>>(p);
     } else
         strict::rk45_integrate<<<integrate_blocks, strict::RK_THREADS, strict::RK_SMEM_BYTES, s>>>(p);
 }
@@ -46,6 +46,7 @@ void launch_rk4_strict(const RunParams &p, cudaStream_t s)
     }
 }
 
+int threads_rk45_strict(bool coop) { return coop ? strict::CO_THREADS : strict::RK_THREADS; }
 int occupancy_rk45_strict(bool coop)
 {
     int nb = 0;
@@ -53,7 +54,7 @@ int occupancy_rk45_strict(bool coop)
         cudaFuncSetAttribute(strict::rk45_integrate_coop<OUT_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::CO_SMEM_BYTES);
         cudaFuncSetAttribute(strict::rk45_integrate_coop<OUT_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::CO_SMEM_BYTES);
         cudaFuncSetAttribute(strict::rk45_integrate_coop<OUT_ROWS | OUT_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, strict::CO_SMEM_BYTES);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, strict::rk45_integrate_coop<OUT_ROWS>, strict::RK_THREADS, strict::CO_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, strict::rk45_integrate_coop<OUT_ROWS>, strict::CO_THREADS, strict::CO_SMEM_BYTES);
 #if RWRT_TMEM_KS
         // the occupancy calculator answers 1 for a kernel that allocates tensor memory (it cannot know how many
         // columns tcgen05.alloc will ask for); this build takes 64 of the 512 columns per block
