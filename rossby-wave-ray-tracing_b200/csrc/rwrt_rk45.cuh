@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(128) rk45_prepare(RunParams p)
     st[14] = y[1];
     reinterpret_cast<int *>(st + 15)[0] = 0;  // accepted so far
     reinterpret_cast<int *>(st + 15)[1] = 0;  // attempts so far; bit 31 set = ray finished
+    if (p.rows_done) p.rows_done[i] = 1;      // next output row of this ray (the cooperative kernel's progress flag)
 }
 
 // Pre-fill of the output rows 1..nt-1, whole rows, fully coalesced (a streaming write at HBM speed):
@@ -622,6 +623,16 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src, u
 #endif
 }
 
+// Progress flags of the time quanta: release / acquire at GPU scope instead of a full fence on either side (a pick-up
+// is a chain of dependent L2 round trips during which the whole warp waits; MEMBAR.GPU was the longest link).
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+
 // Warp-cooperative request for the four corner points of every lane's cell (used by rk45_integrate_coop and
 // rk4_integrate_coop; expects the kernels' local names: p, FULL, lane_id, grp, q8, member_pt, prev_key, fetch_list,
 // pf_src / pf_dx / pf_dy / pf_dst, l2pol and the outputs inr, x0, y0, x1, y1, sx, sy).
@@ -724,48 +735,73 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
     const unsigned pf_dy = (q8 & 2) ? NPK * 8u : 0u;                      // corners 1, 3 one point further
     const char *pf_src = reinterpret_cast<const char *>(p.g.fpk) + (q8 & 1) * 16 + pf_dx + pf_dy;
 
+    // Work items are (time quantum q, ray r), handed out q-major by one global counter: a ray is integrated a quantum
+    // of output rows at a time, parked (state saved, progress flag set) and picked up again -- by whichever lane is
+    // free -- when its next item comes up.  With whole rays as items the launch ended with a tail of up to one ray
+    // length (3.5 ms of serial work on C2; lanes idled 4.5 % of the time); with quanta the tail is one quantum.  No
+    // barrier separates the quanta: item (q, r) only waits for item (q - 1, r), which was handed out a whole round
+    // earlier.  A waiting lane never spins while other lanes of its warp run (it re-checks once per attempt).
+    // A quantum is a power of two of output rows (p.qmask + 1; 0x7fffffff + 1 = off), counted from the window start, so
+    // that "park here" is a mask test on the row counter and costs no register.  A lane that holds an item it cannot start
+    // yet keeps it in my_ray (L.slot == -2); L.slot == -1: idle without an item.
+    const long long nq = p.nquanta > 1 ? p.nquanta : 1;
+    const unsigned long long total_items = (unsigned long long)p.nlive * (unsigned long long)nq;
     for (;;) {
         __syncwarp();
         // ---- refill idle lanes from the queue (one atomic per warp) ----
-        bool idle = (L.slot < 0);
-        unsigned idle_mask = __ballot_sync(FULL, idle);
-        if (idle_mask == FULL && queue_empty) break;
-        if (idle_mask != 0 && !queue_empty) {
-            int leader = __ffs(idle_mask) - 1;
+        const bool want = (L.slot == -1);
+        const unsigned want_mask = __ballot_sync(FULL, want);
+        if (want_mask == FULL && queue_empty) break;                       // no lane has a ray or holds an item, nothing left to draw
+        if (want_mask != 0 && !queue_empty) {
+            int leader = __ffs(want_mask) - 1;
             unsigned long long base = 0;
-            if (lane_id == leader) base = atomicAdd(p.queue, (unsigned long long)__popc(idle_mask));
+            if (lane_id == leader) base = atomicAdd(p.queue, (unsigned long long)__popc(want_mask));
             base = __shfl_sync(FULL, base, leader);
-            if (base >= (unsigned long long)p.nlive) queue_empty = true;
-            if (idle) {
-                unsigned long long mine = base + __popc(idle_mask & ((1u << lane_id) - 1));
-                if (mine < (unsigned long long)p.nlive) {
-                    const double *st = p.state + (size_t)mine * RWRT_STATE;
-                    const int att0 = reinterpret_cast<const int *>(st + 15)[1];
-                    if (att0 >= 0) {  // not finished in an earlier time window
-                        my_ray = (long long)mine;
-                        L.slot = p.live[mine];
-#pragma unroll
-                        for (int c = 0; c < 5; ++c) {
-                            L.y[c] = st[c];
-                            k1[c] = st[5 + c];
-                        }
-                        L.h_abs = st[10];
-                        pcos = st[11];
-                        L.t = st[12];
-                        L.plon = st[13];
-                        L.plat = st[14];
-                        L.acc = reinterpret_cast<const int *>(st + 15)[0];
-                        acc0 = L.acc;
-                        L.att = att0;
-                        L.it = p.it_begin;
-                        L.rejected = false;
-                        L.fresh = true;
-                        fb = member_base(p, L.slot);
-                        member_pt = (unsigned)((fb - p.g.fpk) / NPK);
-                    }
+            if (base >= total_items) queue_empty = true;
+            if (want) {
+                const unsigned long long id = base + __popc(want_mask & ((1u << lane_id) - 1));
+                if (id < total_items) {
+                    my_ray = (long long)id;
+                    L.slot = -2;
                 }
             }
         }
+        if (L.slot == -2) {
+            const long long q = my_ray / p.nlive, mine = my_ray - q * p.nlive;
+            const double *st = p.state + (size_t)mine * RWRT_STATE;
+            // both flags in one round trip: finished (sign bit of the attempt counter) / parked at row rows_done
+            const int att0 = ld_acquire(reinterpret_cast<const int *>(st + 15) + 1);
+            const int rd = ld_acquire(p.rows_done + mine);
+            const long long b0l = (long long)p.it_begin + q * ((long long)p.qmask + 1);
+            const int b0 = (int)(b0l < p.it_end ? b0l : p.it_end);
+            if (att0 < 0 || b0 >= p.it_end) {
+                L.slot = -1;                                               // the ray finished / died earlier (or a quantum beyond the window)
+            } else if (rd == b0) {   // parked exactly at this quantum's start: its state, written before the flag, is visible (acquire)
+                my_ray = mine;
+                L.slot = p.live[mine];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    L.y[c] = __ldcg(st + c);
+                    k1[c] = __ldcg(st + 5 + c);
+                }
+                L.h_abs = __ldcg(st + 10);
+                pcos = __ldcg(st + 11);
+                L.t = __ldcg(st + 12);
+                L.plon = __ldcg(st + 13);
+                L.plat = __ldcg(st + 14);
+                L.acc = __ldcg(reinterpret_cast<const int *>(st + 15));
+                acc0 = L.acc;
+                L.att = att0;
+                L.it = b0;
+                L.rejected = false;
+                L.fresh = true;
+                fb = member_base(p, L.slot);
+                member_pt = (unsigned)((fb - p.g.fpk) / NPK);
+            }
+        }
+        // (A warp whose lanes only WAIT for rays that other warps are still integrating runs an attempt on the benign idle
+        // state: an early `continue` / a second exit test here makes ptxas guard every __syncwarp and tcgen05 instruction of
+        // the stage loop with BRA.DIV + WARPSYNC, which costs 9 %.)
         const bool active = (L.slot >= 0);
 
         // ---- one attempt (rkf45.py:410-502); idle lanes run along on a benign state (they serve the gathers) ----
@@ -997,14 +1033,14 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
             ++L.it;
         }
         const bool finished = dead || L.it >= p.nt;
-        if (finished || L.it >= p.it_end) {  // ray finished, or parked at the end of this time window
+        if (finished || L.it >= p.it_end || ((L.it - p.it_begin) & p.qmask) == 0) {  // finished, or parked at the end of its time quantum / window
             double *st = p.state + (size_t)my_ray * RWRT_STATE;
-            if (p.rows_done) p.rows_done[my_ray] = L.it;                  // rows 0 .. L.it-1 of this ray are valid
             if (finished) {
                 if (p.accepted) p.accepted[L.slot] = L.acc;
                 if (p.attempts) p.attempts[L.slot] = L.att;
                 if (p.status) p.status[L.slot] = (signed char)code;
-                reinterpret_cast<int *>(st + 15)[1] = L.att | (int)0x80000000;
+                p.rows_done[my_ray] = L.it;                               // rows 0 .. L.it-1 of this ray are valid
+                st_release(reinterpret_cast<int *>(st + 15) + 1, L.att | (int)0x80000000);
             } else {
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -1018,6 +1054,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
                 st[14] = L.plat;
                 reinterpret_cast<int *>(st + 15)[0] = L.acc;
                 reinterpret_cast<int *>(st + 15)[1] = L.att;
+                st_release(p.rows_done + my_ray, L.it);                   // parked (the state before the flag): the next quantum's item may start
             }
             my_total += L.acc - acc0;
             L.slot = -1;
