@@ -733,7 +733,7 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
     p.rec_rows = 0;
     p.rec_it0 = 1;
     p.nquanta = 1;
-    p.qmask = 0x7fffffff;
+    p.qshift = 0;
     p.rows_done = nullptr;
     p.inv = nullptr;
     int per_sm = strict ? occupancy_rk45_strict(coop) : occupancy_rk45_fast(coop);
@@ -785,12 +785,14 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         if (h->rows_done.reserve((size_t)nlive * sizeof(int32_t))) return fail(RWRT_ERR_NOMEM, "ray progress flags (%llu rays)", nlive);
         p.rows_done = (int32_t *)h->rows_done.p;
     }
-    // Time quanta inside a launch: a ray is integrated a power-of-two number of output rows at a time and re-queued, so that the
-    // persistent grid ends with a tail of one quantum instead of one whole ray.  Measured on C2 (integrate kernel, 360 rows per
-    // ray, 10 rays per lane): off 45.8 ms, 32 rows 44.4, 64: 42.9, 128: 42.5, 256: 41.9 -- every pick-up is three dependent L2
-    // round trips during which the whole warp waits, so few large quanta win.  RWRT_QUANTUM_ROWS=0 switches them off.
-    int quantum_rows = 256;
-    if (const char *e = getenv("RWRT_QUANTUM_ROWS")) quantum_rows = atoi(e);
+    // Time quanta inside a launch: a ray is integrated a quantum of output rows at a time and re-queued, so that the persistent
+    // grid ends with a tail of one (short) quantum instead of one whole ray -- and rays differ a lot in length.  The quanta
+    // shrink geometrically (by 2^RWRT_QUANTUM_SHIFT, default 4x) down to RWRT_QUANTUM_MIN rows.  RWRT_QUANTUM_SHIFT=0: off.
+    int qshift = 2, qmin = 8;
+    if (const char *e = getenv("RWRT_QUANTUM_SHIFT")) qshift = atoi(e);
+    if (const char *e = getenv("RWRT_QUANTUM_MIN")) qmin = atoi(e);
+    if (qshift < 0 || qshift > 8) qshift = 0;
+    if (qmin < 1) qmin = 1;
     // window bounds: rows [bounds[w], bounds[w + 1]) belong to window w.  Host delivery: the first and the last window
     // are split (1/4, 1/4, 1/2) so that the pipeline fills and drains on quarter-size windows -- the host threads start
     // after a quarter of a window has been integrated, packed and copied, and finish a quarter window after the last copy.
@@ -832,14 +834,10 @@ static int run_rk45(rwrt_handle h, int nsource, const int32_t *src_member, int n
         p.it_begin = bounds[w];
         p.it_end = bounds[w + 1];
         p.rec_it0 = p.it_begin;                     // record row r of this window is output row it_begin + r
-        p.qmask = 0x7fffffff;                       // quanta off: one work item per ray and window
-        p.nquanta = 1;
-        if (quantum_rows > 0 && quantum_rows < p.it_end - p.it_begin) {
-            int q2 = 1;
-            while (q2 * 2 <= quantum_rows) q2 *= 2;  // power of two <= RWRT_QUANTUM_ROWS
-            p.qmask = q2 - 1;
-            p.nquanta = (p.it_end - p.it_begin + q2 - 1) / q2;
-        }
+        p.qshift = qshift;
+        p.nquanta = 1;                              // quanta off: one work item per ray and window
+        if (qshift > 0)                             // quantum q + 1 exists while the rows left after quantum q are >= qmin
+            while (p.nquanta < 15 && qshift * p.nquanta < 31 && ((p.it_end - p.it_begin) >> (qshift * p.nquanta)) >= qmin) ++p.nquanta;
         if (w > 0) CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));  // rewind the work queue
         cudaEvent_t *we = win_events(h, w);
         if (we) CU(cudaEventRecord(we[0], s));

@@ -741,11 +741,15 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
     // length (3.5 ms of serial work on C2; lanes idled 4.5 % of the time); with quanta the tail is one quantum.  No
     // barrier separates the quanta: item (q, r) only waits for item (q - 1, r), which was handed out a whole round
     // earlier.  A waiting lane never spins while other lanes of its warp run (it re-checks once per attempt).
-    // A quantum is a power of two of output rows (p.qmask + 1; 0x7fffffff + 1 = off), counted from the window start, so
-    // that "park here" is a mask test on the row counter and costs no register.  A lane that holds an item it cannot start
-    // yet keeps it in my_ray (L.slot == -2); L.slot == -1: idle without an item.
+    // The quanta shrink geometrically: quantum q ends where all but 1 / 2^(qshift (q + 1)) of the window's rows are done
+    // (with qshift = 2: 3/4 of the rows, then 3/16, 3/64 ...).  Few pick-ups per ray (each is three dependent L2 round trips
+    // during which the whole warp waits), yet the LAST items -- the ones that make the tail, and rays differ: 3 % of the
+    // 0.25-degree rays take more than twice the mean number of steps, one in 10^6 seven times -- are a few rows long.
+    // A lane that holds an item it cannot start yet keeps it in my_ray (L.slot == -2); L.slot == -1: idle without an item.
     const long long nq = p.nquanta > 1 ? p.nquanta : 1;
     const unsigned long long total_items = (unsigned long long)p.nlive * (unsigned long long)nq;
+    const int win_len = p.it_end - p.it_begin;
+    int it_stop = p.it_end;                                                // this lane's ray parks before output row it_stop
     for (;;) {
         __syncwarp();
         // ---- refill idle lanes from the queue (one atomic per warp) ----
@@ -772,12 +776,13 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
             // both flags in one round trip: finished (sign bit of the attempt counter) / parked at row rows_done
             const int att0 = ld_acquire(reinterpret_cast<const int *>(st + 15) + 1);
             const int rd = ld_acquire(p.rows_done + mine);
-            const long long b0l = (long long)p.it_begin + q * ((long long)p.qmask + 1);
-            const int b0 = (int)(b0l < p.it_end ? b0l : p.it_end);
-            if (att0 < 0 || b0 >= p.it_end) {
-                L.slot = -1;                                               // the ray finished / died earlier (or a quantum beyond the window)
+            const int b0 = p.it_begin + win_len - (win_len >> (p.qshift * (int)q));            // q = 0: the window start
+            const int b1 = (q + 1 >= nq) ? p.it_end : p.it_begin + win_len - (win_len >> (p.qshift * ((int)q + 1)));
+            if (att0 < 0 || b1 <= b0) {
+                L.slot = -1;                                               // the ray finished / died earlier (or an empty quantum)
             } else if (rd == b0) {   // parked exactly at this quantum's start: its state, written before the flag, is visible (acquire)
                 my_ray = mine;
+                it_stop = b1;
                 L.slot = p.live[mine];
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -791,7 +796,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
                 L.plat = __ldcg(st + 14);
                 L.acc = __ldcg(reinterpret_cast<const int *>(st + 15));
                 acc0 = L.acc;
-                L.att = att0;
+                L.att = __ldcg(reinterpret_cast<const int *>(st + 15) + 1);   // (att0 was read before the flag: only its sign is used)
                 L.it = b0;
                 L.rejected = false;
                 L.fresh = true;
@@ -1033,7 +1038,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
             ++L.it;
         }
         const bool finished = dead || L.it >= p.nt;
-        if (finished || L.it >= p.it_end || ((L.it - p.it_begin) & p.qmask) == 0) {  // finished, or parked at the end of its time quantum / window
+        if (finished || L.it >= it_stop) {  // finished, or parked at the end of its time quantum / this time window
             double *st = p.state + (size_t)my_ray * RWRT_STATE;
             if (finished) {
                 if (p.accepted) p.accepted[L.slot] = L.acc;

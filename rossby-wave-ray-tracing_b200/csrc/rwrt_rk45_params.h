@@ -29,7 +29,8 @@ struct RunParams {
     int32_t *rows_done;         // (nlive): number of valid rows 0..rows_done-1 of a ray so far
     const int32_t *inv;         // (N): slot -> index in the live list, -1 for NaN-root slots
     int it_begin, it_end;       // this launch produces output rows [it_begin, it_end) (time window)
-    int nquanta, qmask;         // the cooperative kernel integrates a ray qmask + 1 (a power of two) output rows at a time: nquanta work items per ray
+    int nquanta, qshift;        // the cooperative kernel integrates a ray in nquanta time quanta (work items); quantum q ends at row
+                                // it_begin + len - (len >> qshift (q + 1)), the last one at it_end
     long long *accepted;        // (N) or nullptr
     long long *attempts;        // (N) or nullptr
     signed char *status;        // (N) or nullptr
