@@ -608,6 +608,10 @@ __device__ __forceinline__ void tm_combo(unsigned tk, const double *k1, const do
 #ifndef RWRT_L2_HINT
 #define RWRT_L2_HINT 1
 #endif
+#ifndef RWRT_CP_CG
+#define RWRT_CP_CG 0     // 1: the gathers bypass L1 (cp.async.cg: LDGSTS.BYPASS).  Measured: C2 (1 degree) 41.17 -> 41.00 ms, but C5 (0.25
+                         // degree) 1258 -> 1343 ms: there the stages of a step straddle cell edges and L1 serves the re-fetches
+#endif
 __device__ __forceinline__ unsigned long long l2_policy_evict_last()
 {
     unsigned long long pol;
@@ -616,7 +620,9 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_last()
 }
 __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src, unsigned long long pol)
 {
-#if RWRT_L2_HINT
+#if RWRT_L2_HINT && RWRT_CP_CG
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "l"(pol));
+#elif RWRT_L2_HINT
     asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "l"(pol));
 #else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src));
