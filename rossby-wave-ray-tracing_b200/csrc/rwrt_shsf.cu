@@ -15,6 +15,7 @@
 // fp64 by contract).  Tables are computed on the host in extended precision when the plan is created.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -91,11 +92,106 @@ __global__ void __launch_bounds__(256) gemm_f64_strided(GemmArgs g)
     }
 }
 
+// The same product on the FP64 tensor-core path: mma.sync m8n8k4 (DMMA).  The CUDA-core kernel above needs one LDS.64
+// per two DFMA (4 x 4 outputs per thread) and reached 25-33 % of the DFMA peak, bound by the shared-memory pipe; here a
+// warp owns a 32 x 32 tile = 4 x 4 fragments of 8 x 8, and every k-step of 4 costs each thread 8 LDS.64 for 16 DMMA
+// (= 128 FMA per thread): 1/8 of the shared-memory traffic per flop, 1/8 of the issue slots.  Same arguments, strides and
+// tile loads; fragments come straight from the k-major tiles, whose row stride (tile + 4 doubles) makes the
+// (lane & 3, lane >> 2) access pattern of a half-warp hit 16 distinct 8-byte banks.  (tcgen05 has no FP64 kind: for
+// double precision mma.sync IS the tensor-core path on sm_100a.)
+constexpr int MPAD = 4;
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(128) gemm_f64_mma(GemmArgs g)
+{
+    // two tile buffers: the next k-tile is fetched into registers before the current one is multiplied and stored to the
+    // other buffer afterwards -- global-load latency hides behind 64 DMMA per warp, one __syncthreads per k-tile
+    __shared__ double As[2][TK][TM + MPAD];
+    __shared__ double Bs[2][TK][TN + MPAD];
+    const int b = blockIdx.z;
+    const int ab = g.a_bmod > 0 ? b % g.a_bmod : b;
+    const double *A = g.A + (long long)ab * g.sa_b;
+    const double *B = g.B + (long long)b * g.sb_b;
+    double *C = g.C + (long long)b * g.sc_b;
+    const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;          // this warp's 32 x 32 corner of the 64 x 64 tile
+    const int fk = lane & 3, fr = lane >> 2;                         // fragment coordinates of this lane
+    // this thread's 8 + 8 tile elements e = tid + 128 r: consecutive threads run along whichever index is contiguous in
+    // memory, so (row, k) of element r is (tid / 16 + 8 r, tid % 16) or (tid % 64, tid / 64 + 2 r) -- one base pointer and
+    // one stride per operand, everything else is recomputed from r (keeps the kernel at 4 blocks per SM)
+    constexpr int EPT = TM * TK / 128;
+    const bool a_kfast = (g.sa_k == 1), b_kfast = (g.sb_k == 1);
+    const int t16 = threadIdx.x & 15, t64 = threadIdx.x & 63, q16 = threadIdx.x >> 4, q64 = threadIdx.x >> 6;
+    const double *pa = a_kfast ? A + (long long)(i0 + q16) * g.sa_i + t16 : A + (long long)(i0 + t64) * g.sa_i + (long long)q64 * g.sa_k;
+    const double *pb = b_kfast ? B + (long long)(j0 + q16) * g.sb_j + t16 : B + (long long)(j0 + t64) * g.sb_j + (long long)q64 * g.sb_k;
+    const long long sta = a_kfast ? 8 * g.sa_i : 2 * g.sa_k, stb = b_kfast ? 8 * g.sb_j : 2 * g.sb_k;
+    double ra[EPT], rb[EPT];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const int ai = a_kfast ? q16 + 8 * r : t64, ak = a_kfast ? t16 : q64 + 2 * r;
+            const int bj = b_kfast ? q16 + 8 * r : t64, bk = b_kfast ? t16 : q64 + 2 * r;
+            ra[r] = (i0 + ai < g.M && k0 + ak < g.K) ? pa[r * sta + (long long)k0 * g.sa_k] : 0.0;
+            rb[r] = (j0 + bj < g.N && k0 + bk < g.K) ? pb[r * stb + (long long)k0 * g.sb_k] : 0.0;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const int ai = a_kfast ? q16 + 8 * r : t64, ak = a_kfast ? t16 : q64 + 2 * r;
+            const int bj = b_kfast ? q16 + 8 * r : t64, bk = b_kfast ? t16 : q64 + 2 * r;
+            As[buf][ak][ai] = ra[r];
+            Bs[buf][bk][bj] = rb[r];
+        }
+    };
+    double acc[4][4][2] = {};
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < g.K; k0 += TK) {
+        const bool more = k0 + TK < g.K;
+        if (more) fetch(k0 + TK);
+#pragma unroll
+        for (int ks = 0; ks < TK; ks += 4) {
+            double a[4], bb[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[buf][ks + fk][wm + 8 * mi + fr];      // A fragment: row fr, column fk of the 8 x 4 block
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) bb[ni] = Bs[buf][ks + fk][wn + 8 * ni + fr];     // B fragment: row fk, column fr of the 4 x 8 block
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+        }
+        if (more) stash(buf ^ 1);        // the other buffer: its last readers passed the barrier of the previous iteration
+        __syncthreads();
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int gi = i0 + wm + 8 * mi + fr;                       // C fragment: row fr, columns 2 fk and 2 fk + 1
+        if (gi >= g.M) continue;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int gj = j0 + wn + 8 * ni + 2 * fk + h;
+                if (gj < g.N) C[gi * g.sc_i + gj * g.sc_j] = acc[mi][ni][h];
+            }
+    }
+}
+
 int launch_gemm(const GemmArgs &g, cudaStream_t s)
 {
     if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return 0;
     dim3 grid((g.N + TN - 1) / TN, (g.M + TM - 1) / TM, g.batch);
-    gemm_f64_strided<<<grid, 256, 0, s>>>(g);
+    static const bool dfma = [] { const char *e = getenv("RWRT_SHSF_GEMM"); return e && !strcmp(e, "dfma"); }();   // cross-check path
+    if (dfma) gemm_f64_strided<<<grid, 256, 0, s>>>(g);
+    else gemm_f64_mma<<<grid, 128, 0, s>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
