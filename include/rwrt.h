@@ -237,7 +237,8 @@ int rwrt_host_expand_rows(double *out7_host, int nt, int64_t nslot, const int32_
 int rwrt_trim(rwrt_handle h);
 
 /* counters of the last rwrt_ray_run_rk45 on this handle (host side, after a sync):
- * [0] kernels launched, [1] live rays, [2] ms of the integrate kernel(s) by CUDA events */
+ * [0] kernels launched, [1] live rays, [2] ms of the whole run (first kernel after the live-ray compaction to the last one)
+ * by CUDA events on the launching stream; rwrt_last_run_times splits it */
 int rwrt_last_run_stats(rwrt_handle h, double *stats3);
 
 /* CUDA-event times of the last run on this handle (ms, after a sync): [0] whole run (as stats3[2]), [1] the integrate

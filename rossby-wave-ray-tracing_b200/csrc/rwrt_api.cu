@@ -343,6 +343,9 @@ int rwrt_create(int device, int nlon, int nlat, int xcyclic, int nmember, rwrt_h
     if (!out) return fail(RWRT_ERR_ARG, "out handle is NULL");
     *out = nullptr;
     if (nlon < 2 || nlat < 3 || nmember < 1) return fail(RWRT_ERR_ARG, "need nlon >= 2, nlat >= 3, nmember >= 1");
+    // the basic-state kernels put the longitude index on gridDim.y and the ensemble member on gridDim.z
+    if (nlon + 1 > 65535 || nmember > 65535)
+        return fail(RWRT_ERR_ARG, "nlon (%d) and nmember (%d) must be below 65535 (grid dimensions of the stencil kernels): split the ensemble over handles", nlon, nmember);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();

@@ -219,3 +219,30 @@ def test_results_on_device_are_fetched_not_nan(recwarn):
     w3.ray_run(mode="numpy", inte_method="rk45", to_host=False)
     with pytest.warns(RuntimeWarning):
         w3.clean()
+
+
+def test_wn_grid_maps_equal_ray_init_of_the_oracle():
+    """`WN.cal_wave` (wn.py:58-87 as intended; parity unpinned: the reference's method never runs): maps of l, root
+    count, ug, vg at every grid point == the oracle's t = 0 state for sources at the grid points."""
+    from rwrt_b200.wn import WN
+    from oracle import oracle
+    u, v = synthetic.clim(144, 73)
+    lon, lat = synthetic.grid_coords(144, 73)
+    zwn = np.array([1.0, 3.0, 6.0])
+    wn = WN(144, 73, 3, freq=2 * np.pi / (40 * 86400.0))
+    wn.bs.lon, wn.bs.lat, wn.bs.u, wn.bs.v = lon, lat, u, v
+    wn.bs.ready(xcyclic=True)
+    wn.set_zwn(zwn)
+    wn.cal_wave()
+    F = oracle.bs_ready(u, v, lat, True, np.cos(lat), np.sin(lat))
+    ref = oracle.ray_init(F, lon, lat, np.repeat(lon, 73), np.tile(lat, 144), zwn, wn.freq, 1)[:, 0]     # (7, 3, ns, nz)
+    l_ref = np.moveaxis(ref[3], 0, -1).reshape(144, 73, 3, 3)
+    assert wn.mwn.shape == (144, 73, 3, 3) and wn.rootnum.shape == (144, 73, 3)
+    assert np.array_equal(np.isnan(wn.mwn), np.isnan(l_ref))
+    np.testing.assert_allclose(wn.mwn, l_ref, rtol=1e-12, equal_nan=True)
+    assert np.array_equal(wn.rootnum, (~np.isnan(l_ref)).sum(-1))
+    ug_ref = np.where(np.isnan(l_ref), 0.0, np.moveaxis(ref[5], 0, -1).reshape(144, 73, 3, 3))
+    np.testing.assert_allclose(wn.ug, ug_ref, rtol=1e-10, atol=1e-12)
+    assert wn.rootnum.max() == 3 and wn.rootnum.min() == 0 and (wn.rootnum[:, 0] == 0).all()     # nothing propagates at the pole rows
+    with pytest.raises(ValueError):
+        wn.set_zwn([1.0])
