@@ -1251,6 +1251,9 @@ int rwrt_last_run_stats(rwrt_handle h, double *stats3)
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         stats3[2] = ms;
+        unsigned long long lost = 0;     // counters[3]: the integrator's watchdog (a ray's progress flag never arrived)
+        CU(cudaMemcpy(&lost, (const unsigned long long *)h->counters.p + 3, sizeof lost, cudaMemcpyDeviceToHost));
+        if (lost) return fail(RWRT_ERR_CUDA, "rwrt_last_run_stats: the integrator gave up waiting for a ray's previous time quantum; the results of this run are incomplete");
     }
     return RWRT_OK;
 }

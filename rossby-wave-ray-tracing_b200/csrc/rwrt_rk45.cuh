@@ -773,6 +773,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
                 if (id < total_items) {
                     my_ray = (long long)id;
                     L.slot = -2;
+                    L.acc = 0;                                             // (idle lanes: counts the attempts spent waiting, see below)
                 }
             }
         }
@@ -808,6 +809,13 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
                 L.fresh = true;
                 fb = member_base(p, L.slot);
                 member_pt = (unsigned)((fb - p.g.fpk) / NPK);
+            } else if (++L.acc > (1 << 21)) {
+                // Watchdog: the previous quantum of this ray is at most one quantum of integration away (tens of ms); two
+                // million attempts (> 10 s) of waiting can only mean a lost progress flag.  Give the item up and raise the
+                // flag the host checks (rwrt_last_run_stats fails) instead of hanging the device.  (No trap here: an exit
+                // path in this region costs ptxas its convergence proof for the stage loop, like the early `continue`.)
+                p.queue[3] = 1ull;
+                L.slot = -1;
             }
         }
         // (A warp whose lanes only WAIT for rays that other warps are still integrating runs an attempt on the benign idle

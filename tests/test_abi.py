@@ -144,3 +144,34 @@ def test_host_expand_rows_equals_restatement(L, monkeypatch, isa, nslot, nt, b, 
     # argument errors: row 0 is not produced here; rows must exist
     assert L.rwrt_host_expand_rows(lib.ptr(out), nt, nslot, lib.ptr(inv), lib.ptr(packed), nlive, 0, e, 0, nslot) != 0
     assert L.rwrt_host_expand_rows(lib.ptr(out), nt, nslot, lib.ptr(inv), lib.ptr(packed), nlive, 1, nt + 1, 0, nslot) != 0
+
+
+def test_stage_loop_of_the_integrator_has_no_divergence_guards(L):
+    """Code-generation guard (CPU, via cuobjdump): the stage loop of fast::rk45_integrate_coop must contain no
+    WARPSYNC.ALL / BRA.DIV.  When ptxas cannot prove the warp converged there (an early `continue`, a `trap` or a second
+    exit test in the refill section did that in round 2), it guards every __syncwarp / tcgen05 instruction of the loop and
+    the kernel loses 9 % with bit-identical results -- invisible to every parity test."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    for out_mode in (1, 2, 3):
+        fn = f"_ZN4rwrt4fast19rk45_integrate_coopILi{out_mode}EEEvNS_9RunParamsE"
+        sass = subprocess.run([cuobjdump, "-sass", "-fun", fn, lib.LIB_PATH], capture_output=True, text=True).stdout
+        rows = [(int(m.group(1), 16), m.group(2)) for m in re.finditer(r"/\*([0-9a-f]{4,5})\*/\s+(.*?);", sass)]
+        assert len(rows) > 2000, "integrator SASS not found"
+        sttm = [i for i, (_, t) in enumerate(rows) if "STTM" in t]
+        assert sttm, "the stage vectors no longer go to tensor memory?"
+        lo = hi = None
+        for i in range(sttm[0], min(sttm[0] + 80, len(rows))):          # the loop's back edge follows the STTM of stage s
+            m = re.search(r"BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)", rows[i][1])
+            if m and int(m.group(1), 16) < rows[i][0]:
+                lo, hi = int(m.group(1), 16), rows[i][0]
+                break
+        assert lo is not None, "stage loop not found"
+        body = [t for a, t in rows if lo <= a <= hi]
+        assert 500 < len(body) < 800, len(body)
+        guards = [t for t in body if "WARPSYNC" in t or "BRA.DIV" in t]
+        assert not guards, f"OUT={out_mode}: {len(guards)} divergence guards in the stage loop: {guards[:3]}"
+        assert sum("DFMA" in t for t in body) > 100 and sum("LDGSTS" in t for t in body) >= 3
