@@ -631,10 +631,21 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src, u
 
 // Progress flags of the time quanta: release / acquire at GPU scope instead of a full fence on either side (a pick-up
 // is a chain of dependent L2 round trips during which the whole warp waits; MEMBAR.GPU was the longest link).
+// The reader does NOT use ld.acquire: that compiles to CCTL.IVALL (the whole L1 is invalidated on every pick-up, and at
+// 0.25 degree L1 serves a good part of the gathers).  It reads the flags with ld.relaxed.gpu (served by L2) and everything
+// the flag guards with ld.global.cg (__ldcg: L2 only, never L1), issued after the branch on the flag value -- no stale L1
+// line can be consulted, and a load is not issued before the branch it depends on has resolved.
+#ifndef RWRT_FLAG_ACQUIRE
+#define RWRT_FLAG_ACQUIRE 0
+#endif
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
     int v;
+#if RWRT_FLAG_ACQUIRE
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+#else
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+#endif
     return v;
 }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
