@@ -635,6 +635,9 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src, u
 // 0.25 degree L1 serves a good part of the gathers).  It reads the flags with ld.relaxed.gpu (served by L2) and everything
 // the flag guards with ld.global.cg (__ldcg: L2 only, never L1), issued after the branch on the flag value -- no stale L1
 // line can be consulted, and a load is not issued before the branch it depends on has resolved.
+#ifndef RWRT_TK_OPAQUE
+#define RWRT_TK_OPAQUE 1
+#endif
 #ifndef RWRT_FLAG_ACQUIRE
 #define RWRT_FLAG_ACQUIRE 0
 #endif
@@ -703,7 +706,11 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
-    const int lane_id = tid & 31, warp_id = tid >> 5;
+    int lane_id = tid & 31;
+    const int warp_id = tid >> 5;
+#if RWRT_TK_OPAQUE
+    asm volatile("" : "+r"(lane_id));                                      // opaque: ptxas re-derived it from %tid (S2R, ~25 cycles) in every stage
+#endif
     unsigned char *stage = smem_raw + warp_id * CO_STAGE_BYTES;            // this warp's 32 x 384 B
     const unsigned stage_u32 = (unsigned)__cvta_generic_to_shared(stage);
 #if RWRT_TMEM_KS
@@ -720,7 +727,12 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const unsigned tm_base = *tm_slot;
+#if RWRT_TK_OPAQUE
+    unsigned tk = tm_base + ((unsigned)(warp_id * 32) << 16);             // + 10 * (s - 1): K_{s+1}, s = 1..5
+    asm volatile("" : "+r"(tk));                                           // opaque: kept in a register instead of being recomputed from %tid (S2R) in every stage
+#else
     const unsigned tk = tm_base + ((unsigned)(warp_id * 32) << 16);       // + 10 * (s - 1): K_{s+1}, s = 1..5
+#endif
 #else
     double *ks = reinterpret_cast<double *>(smem_raw + (CO_THREADS / 32) * CO_STAGE_BYTES);
 #define KS(s, c) ks[(((s) - 1) * 5 + (c)) * CO_THREADS + tid]            /* K2..K6 <-> s = 1..5 */
