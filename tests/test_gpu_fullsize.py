@@ -219,3 +219,106 @@ def test_host_entry_quarter_size(monkeypatch):
             assert int(tot_h[0]) == total and np.array_equal(acc_h, acc0) and np.array_equal(st_h, status0), env
     finally:
         L.rwrt_destroy(h)
+
+
+def _sweep(L, h, d, dev, slon, slat, zwn, nt, ttotal, cell, freq=0.0, flags=lib.MODE_FAST, member=None):
+    import torch
+    from rwrt_b200 import gridding
+    ns, nz = len(slon), len(zwn)
+    sl = torch.from_numpy(np.ascontiguousarray(slon)).to(dev)
+    sa = torch.from_numpy(np.ascontiguousarray(slat)).to(dev)
+    zw = torch.from_numpy(np.ascontiguousarray(zwn)).to(dev)
+    mem = None if member is None else torch.from_numpy(np.ascontiguousarray(member, dtype=np.int32)).to(dev)
+    g = gridding.new_grids(*cell, dev)
+    ncx, ncy = gridding.grid_shape(*cell)
+    acc = torch.zeros(3 * ns * nz, dtype=torch.int64, device=dev)
+    tot = torch.zeros(1, dtype=torch.int64, device=dev)
+    lib.check(L.rwrt_ray_sweep_grid(h, ns, lib.ptr(sl), lib.ptr(sa), lib.ptr(mem), nz, lib.ptr(zw), freq, nt, TSTEP, ttotal, 1e-6, 1e-6,
+                                    1e-3, 0.1, flags, cell[0], cell[1], ncx, ncy, lib.ptr(g[0]), lib.ptr(g[1]), lib.ptr(g[2]), lib.ptr(acc),
+                                    None, lib.ptr(tot), lib.stream_ptr()), "rwrt_ray_sweep_grid")
+    torch.cuda.synchronize()
+    return g, acc, int(tot.item())
+
+
+def test_c5_full_size_sweep_is_deterministic_and_independent_of_sharding():
+    """BASELINE configs[4] at FULL size through the north-star path: 1440 x 385 sources x k = 1..6 x 3 roots = 9 979 200 ray
+    slots, 0.25-degree background, 60 days, gridded without any trajectory array (the reference layout would need 403 GB,
+    wr.py:157-167).  The integer grids and the per-slot step counts must be identical from run to run and for the sources split
+    into two strided shards (what `dist.sweep_sharded` gives two ranks), and consistent with each other."""
+    import torch
+    from rwrt_b200 import gridding
+    nlon, nlat = 1440, 721
+    slon_deg, slat_deg = synthetic.all_gridpoint_sources(nlon, nlat, 48.125)
+    zwn = np.arange(1.0, 7.0)
+    ns = len(slon_deg)
+    assert 3 * ns * len(zwn) == 9979200
+    L, h, d, dev = _setup(nlon, nlat, slon_deg[:1], slat_deg[:1], zwn)
+    try:
+        slon, slat = np.radians(slon_deg), np.radians(slat_deg)
+        nt, ttotal, cell = 721, 60 * 86400.0, (0.25, 0.25)
+        g1, a1, t1 = _sweep(L, h, d, dev, slon, slat, zwn, nt, ttotal, cell)
+        assert t1 > 6.0e9 and int(a1.sum().item()) == t1
+        samples = int(g1[0].sum().item())
+        # every output row of a live ray is one sample unless it left the three longitude circles: samples <= steps, and a
+        # ray that is alive for r rows took at least r accepted steps
+        assert 3.0e9 < samples <= t1
+        cs = gridding.checksum(g1)
+        g2, a2, t2 = _sweep(L, h, d, dev, slon, slat, zwn, nt, ttotal, cell)
+        assert t2 == t1 and torch.equal(a1, a2) and torch.equal(g1, g2)
+        del g2, a2
+        tot = torch.zeros_like(g1)
+        steps = 0
+        for r in range(2):
+            gr, ar, tr = _sweep(L, h, d, dev, slon[r::2], slat[r::2], zwn, nt, ttotal, cell)
+            tot += gr
+            steps += tr
+            assert torch.equal(ar.view(3, -1, 6), a1.view(3, ns, 6)[:, r::2, :])
+        assert steps == t1 and torch.equal(tot, g1) and gridding.checksum(tot) == cs
+    finally:
+        L.rwrt_destroy(h)
+
+
+def test_c3_full_size_frequency_sweep_three_gridding_paths_agree():
+    """BASELINE configs[2] at full size: the 100 x 100 source matrix, k = 1..8, periods inf / 50 / 30 / 20 d, 30 days
+    (240 000 ray slots per frequency).  Per frequency the grids from (a) the fused sweep, (b) the per-window ray records and
+    (c) the trajectories of rwrt_ray_run_rk45 (rwrt_grid_accumulate) are the same integers; omega changes them."""
+    import torch
+    from rwrt_b200 import gridding
+    nlon, nlat = 360, 181
+    ix, iy = np.meshgrid(np.arange(100), np.arange(100), indexing="xy")
+    slon_deg, slat_deg = (3.6 * ix.ravel()) % 360.0, -49.5 + 1.0 * iy.ravel()
+    zwn = np.arange(1.0, 9.0)
+    ns, nz = len(slon_deg), len(zwn)
+    assert 3 * ns * nz == 240000
+    L, h, d, dev = _setup(nlon, nlat, slon_deg, slat_deg, zwn)
+    try:
+        slon, slat = np.radians(slon_deg), np.radians(slat_deg)
+        nt, ttotal, cell = 361, 30 * 86400.0, (1.0, 1.0)
+        ncx, ncy = gridding.grid_shape(*cell)
+        seen = []
+        for period in (np.inf, 50.0, 30.0, 20.0):
+            freq = 0.0 if np.isinf(period) else 2 * np.pi / (period * 86400.0)
+            g_fused, acc, tot = _sweep(L, h, d, dev, slon, slat, zwn, nt, ttotal, cell, freq)
+            g_rec, acc2, tot2 = _sweep(L, h, d, dev, slon, slat, zwn, nt, ttotal, cell, freq, flags=lib.MODE_FAST | lib.GRID_FROM_RECORDS)
+            assert tot2 == tot and torch.equal(acc, acc2) and torch.equal(g_fused, g_rec)
+            N = 3 * ns * nz
+            out = torch.empty((7, nt, N), dtype=torch.float64, device=dev)
+            sp = lib.stream_ptr()
+            lib.check(L.rwrt_ray_init(h, ns, lib.ptr(d["slon"]), lib.ptr(d["slat"]), None, nz, lib.ptr(d["zwn"]), freq, nt, lib.ptr(out), sp))
+            lib.check(L.rwrt_ray_run_rk45(h, ns, None, nz, nt, TSTEP, ttotal, 1e-6, 1e-6, 1e-3, 0.1, lib.MODE_FAST, lib.ptr(out), None, None,
+                                          None, None, sp))
+            g_pl = gridding.new_grids(*cell, dev)
+            lib.check(L.rwrt_grid_accumulate(h, N, nt, lib.ptr(out), cell[0], cell[1], ncx, ncy, lib.ptr(g_pl[0]), lib.ptr(g_pl[1]),
+                                             lib.ptr(g_pl[2]), sp))
+            torch.cuda.synchronize()
+            assert torch.equal(g_fused, g_pl), period
+            # the grid counts are the finite (lon, lat, l) samples of rows 1.. inside the three longitude circles
+            fin = torch.isfinite(out[0, 1:]) & torch.isfinite(out[1, 1:]) & ~torch.isnan(out[3, 1:])
+            lon_deg = out[0, 1:][fin] * (180.0 / np.pi)
+            assert int(g_fused[0].sum().item()) == int(((lon_deg >= -360.0) & (lon_deg < 720.0)).sum().item())
+            del out, g_pl
+            seen.append(g_fused[0].clone())
+            assert tot > 2.0e7
+        assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[3])     # omega enters the t = 0 cubic (bs.py:1005)
+    finally:
+        L.rwrt_destroy(h)
