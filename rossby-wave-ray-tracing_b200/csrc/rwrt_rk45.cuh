@@ -563,6 +563,16 @@ __device__ __forceinline__ void tm_wait_ld(unsigned (&v)[10])
                  : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
                    "+r"(v[8]), "+r"(v[9]));
 }
+// tcgen05.wait::ld waits for ALL earlier tcgen05.ld of the thread, so one wait serves every vector of a combination;
+// the others only need the ordering (an empty statement that redefines the registers after the wait).  Each extra
+// wait was an issue slot (a NOP carrying the scoreboard wait) in the stage loop.
+#ifndef RWRT_TM_ONEWAIT
+#define RWRT_TM_ONEWAIT 1
+#endif
+__device__ __forceinline__ void tm_bind_ld(unsigned (&v)[10])
+{
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]));
+}
 __device__ __forceinline__ double tm_val(const unsigned (&v)[10], int c) { return __hiloint2double((int)v[2 * c + 1], (int)v[2 * c]); }
 __device__ __forceinline__ void tm_st5(unsigned taddr, const double *k)
 {
@@ -595,7 +605,8 @@ __device__ __forceinline__ void tm_combo(unsigned tk, const double *k1, const do
     for (int c = 0; c < 5; ++c) a[c] = k1[c] * coef[0];
 #pragma unroll
     for (int j = 0; j < S - 1; ++j) {
-        tm_wait_ld(v[j]);
+        if (j == 0 || !RWRT_TM_ONEWAIT) tm_wait_ld(v[j]);
+        else tm_bind_ld(v[j]);
 #pragma unroll
         for (int c = 0; c < 5; ++c) a[c] = a[c] + tm_val(v[j], c) * coef[j + 1];
     }
@@ -653,9 +664,76 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 
+// Which 16-byte piece of a cell a quarter-warp lane copies.  A cell is two runs of 192 contiguous bytes in the point
+// table -- points (x0,y0),(x0,y1) and, one longitude row further, (x1,y0),(x1,y1) -- and they are staged back to back
+// (c | a | d | b, 4 x 96 B), i.e. 24 pieces, piece p at byte 16 p of the staged record.
+//   RWRT_FETCH_MAP 0 (up to v20): lane q8 copies half (q8 & 1) of sector i = 0..2 of corner q8 >> 1: every instruction
+//     touches four separate 32-byte sectors per cell;
+//   RWRT_FETCH_MAP 1: instruction i copies pieces 8 i .. 8 i + 7: 128 contiguous bytes per quarter-warp (i = 1: 64 B of
+//     each run).  tools/experiments/ldgsts_map.cu (the gather alone, 11 cells per warp and stage, 12 warps per SM):
+//     112 -> 73 cycles of the L1 / shared-memory pipe per warp and stage (shared-memory wavefronts of the copies 9.4 -> 6.3
+//     per cell, L1 tag look-ups 10.5 -> 6 per cell).
+#ifndef RWRT_FETCH_MAP
+#define RWRT_FETCH_MAP 1
+#endif
+#if RWRT_FETCH_MAP == 0
+#define RWRT_FETCH_SETUP                                                                                             \
+    /* quarter-warp lane q8 copies 16-byte half (q8 & 1) of sector i = 0..2 of corner point q8 >> 1                 \
+       (0: (x0,y0)  1: (x0,y1)  2: (x1,y0)  3: (x1,y1)); 3 sectors x 32 B = one 96-byte point */                     \
+    const unsigned pf_dst = stage_u32 + (unsigned)((q8 >> 1) * 96 + (q8 & 1) * 16);                                  \
+    const unsigned pf_dx = (q8 & 4) ? (unsigned)p.g.nlat * NPK * 8 : 0u;  /* corners 2, 3 live one longitude row further */ \
+    const unsigned pf_dy = (q8 & 2) ? NPK * 8u : 0u;                      /* corners 1, 3 one point further */        \
+    const char *pf_src = reinterpret_cast<const char *>(p.g.fpk) + (q8 & 1) * 16 + pf_dx + pf_dy;
+#define RWRT_FETCH_COPY(e)                                                                                           \
+    const char *sp = pf_src + (size_t)((e).x & 0x3fffffffu) * (NPK * 8);                                             \
+    if ((e).x >> 30) {                                                      /* clamped: the far corner is the near one */ \
+        if ((e).x & 0x40000000u) sp -= pf_dx;                                                                        \
+        if ((e).x & 0x80000000u) sp -= pf_dy;                                                                        \
+    }                                                                                                                \
+    const unsigned dst = pf_dst + (e).y;                                                                             \
+    cp_async16(dst, sp, l2pol);                                                                                      \
+    cp_async16(dst + 32, sp + 32, l2pol);                                                                            \
+    cp_async16(dst + 64, sp + 64, l2pol);
+#else
+#define RWRT_FETCH_SETUP                                                                                             \
+    /* pieces q8, 8 + q8, 16 + q8 (piece p < 12: run 0 at byte 16 p; p >= 12: run 1 at byte 16 (p - 12)), addressed  \
+       as point index x 96 B + a compile-time offset from ONE per-lane base, so that a copy costs one IMAD.WIDE:      \
+         piece q8      = base + 96 pi                                  (base = table + 16 q8)                        \
+         piece 8 + q8  = base + 96 (pi + d1) + 32       d1 = 1 for q8 < 4 (byte 128 + 16 q8 of run 0),               \
+                                                        nlat - 1 for q8 >= 4 (byte 16 (q8 - 4) of run 1)              \
+         piece 16 + q8 = base + 96 (pi + nlat) + 64     (byte 64 + 16 q8 of run 1) */                                \
+    const unsigned pf_dst = stage_u32 + (unsigned)(q8 * 16);                                                         \
+    const char *pf_src = reinterpret_cast<const char *>(p.g.fpk) + q8 * 16;                                          \
+    unsigned pf_d1 = (q8 < 4) ? 1u : (unsigned)p.g.nlat - 1u;                                                        \
+    asm volatile("" : "+r"(pf_d1), "+l"(pf_src));                           /* kept whole, not re-derived per copy */
+#define RWRT_FETCH_COPY(e)                                                                                           \
+    const unsigned pi = (e).x & 0x3fffffffu;                                                                         \
+    const unsigned dst = pf_dst + (e).y;                                                                             \
+    if (((e).x >> 30) == 0) {                                                                                        \
+        cp_async16(dst, pf_src + (size_t)pi * (NPK * 8), l2pol);                                                     \
+        cp_async16(dst + 128, pf_src + (size_t)(pi + pf_d1) * (NPK * 8) + 32, l2pol);                                \
+        cp_async16(dst + 256, pf_src + (size_t)(pi + (unsigned)p.g.nlat) * (NPK * 8) + 64, l2pol);                   \
+    } else {                                                                                                         \
+        /* clamped (grid edge, NaN position; interpolation.py:116-119): x1 == x0 makes run 1 a copy of run 0,        \
+           y1 == y0 makes a run's second point its first.  Rare; written from scratch so that it shares no register  \
+           with the common path. */                                                                                  \
+        const unsigned xs = ((e).x & 0x40000000u) ? 0u : (unsigned)p.g.nlat, ys = ((e).x & 0x80000000u) ? 0u : 1u;   \
+        int q8r = q8;                                                                                                \
+        asm volatile("" : "+r"(q8r));                                       /* or ptxas keeps this path's per-lane offsets \
+                                                                               in registers for the whole kernel */  \
+        _Pragma("unroll") for (int i_ = 0; i_ < 3; ++i_) {                                                           \
+            const int pc = 8 * i_ + q8r, r_ = pc >= 12 ? 1 : 0, o_ = (pc - 12 * r_) * 16, second = o_ >= 96 ? 1 : 0;  \
+            cp_async16(dst + 128 * i_,                                                                               \
+                       reinterpret_cast<const char *>(p.g.fpk) +                                                     \
+                           (size_t)(pi + (r_ ? xs : 0u) + (second ? ys : 0u)) * (NPK * 8) + (o_ - 96 * second),      \
+                       l2pol);                                                                                       \
+        }                                                                                                            \
+    }
+#endif
+
 // Warp-cooperative request for the four corner points of every lane's cell (used by rk45_integrate_coop and
 // rk4_integrate_coop; expects the kernels' local names: p, FULL, lane_id, grp, q8, member_pt, prev_key, fetch_list,
-// pf_src / pf_dx / pf_dy / pf_dst, l2pol and the outputs inr, x0, y0, x1, y1, sx, sy).
+// the per-lane copy constants of RWRT_FETCH_SETUP, l2pol and the outputs inr, x0, y0, x1, y1, sx, sy).
 #define RWRT_FETCH(LON, LAT)                                                                                         \
     {                                                                                                                \
         inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
@@ -679,15 +757,7 @@ __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.rel
            sectors of corner q8 >> 1 -- 24 x 16 B per cell */                                                        \
         for (int j = grp; j < nfetch; j += 4) {                                                                      \
             const uint2 e = *reinterpret_cast<const uint2 *>(fetch_list + j * CO_LIST_STRIDE);                       \
-            const char *sp = pf_src + (size_t)(e.x & 0x3fffffffu) * (NPK * 8);                                       \
-            if (e.x >> 30) {                                                /* clamped: the far corner is the near one */ \
-                if (e.x & 0x40000000u) sp -= pf_dx;                                                                  \
-                if (e.x & 0x80000000u) sp -= pf_dy;                                                                  \
-            }                                                                                                        \
-            const unsigned dst = pf_dst + e.y;                                                                       \
-            cp_async16(dst, sp, l2pol);                                                                              \
-            cp_async16(dst + 32, sp + 32, l2pol);                                                                    \
-            cp_async16(dst + 64, sp + 64, l2pol);                                                                    \
+            RWRT_FETCH_COPY(e)                                                                                       \
         }                                                                                                            \
         asm volatile("cp.async.commit_group;\n" ::);                                                                 \
     }
@@ -757,12 +827,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
     const unsigned char *my_rec = stage + lane_id * CO_REC_STRIDE;        // this lane's staged cell record
     const unsigned long long l2pol = l2_policy_evict_last();
     unsigned char *fetch_list = stage + CO_LIST_OFS;                       // entry j at fetch_list + j * CO_LIST_STRIDE
-    // quarter-warp lane q8 copies 16-byte half (q8 & 1) of sector i = 0..2 of corner point q8 >> 1
-    // (0: (x0,y0)  1: (x0,y1)  2: (x1,y0)  3: (x1,y1)); 3 sectors x 32 B = one 96-byte point
-    const unsigned pf_dst = stage_u32 + (unsigned)((q8 >> 1) * 96 + (q8 & 1) * 16);
-    const unsigned pf_dx = (q8 & 4) ? (unsigned)p.g.nlat * NPK * 8 : 0u;  // corners 2, 3 live one longitude row further
-    const unsigned pf_dy = (q8 & 2) ? NPK * 8u : 0u;                      // corners 1, 3 one point further
-    const char *pf_src = reinterpret_cast<const char *>(p.g.fpk) + (q8 & 1) * 16 + pf_dx + pf_dy;
+    RWRT_FETCH_SETUP
 
     // Work items are (time quantum q, ray r), handed out q-major by one global counter: a ray is integrated a quantum
     // of output rows at a time, parked (state saved, progress flag set) and picked up again -- by whichever lane is
@@ -1207,10 +1272,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk4_integrate_coop(RunParams p)
     const unsigned char *my_rec = stage + lane_id * CO_REC_STRIDE;
     const unsigned long long l2pol = l2_policy_evict_last();
     unsigned char *fetch_list = stage + CO_LIST_OFS;
-    const unsigned pf_dst = stage_u32 + (unsigned)((q8 >> 1) * 96 + (q8 & 1) * 16);
-    const unsigned pf_dx = (q8 & 4) ? (unsigned)p.g.nlat * NPK * 8 : 0u;
-    const unsigned pf_dy = (q8 & 2) ? NPK * 8u : 0u;
-    const char *pf_src = reinterpret_cast<const char *>(p.g.fpk) + (q8 & 1) * 16 + pf_dx + pf_dy;
+    RWRT_FETCH_SETUP
     unsigned prev_key = 0xffffffffu;
 
     long long slot = (long long)blockIdx.x * blockDim.x + tid;
@@ -1324,6 +1386,8 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk4_integrate_coop(RunParams p)
 }
 
 #undef RWRT_FETCH
+#undef RWRT_FETCH_COPY
+#undef RWRT_FETCH_SETUP
 
 }  // namespace RWRT_VARIANT
 }  // namespace rwrt
