@@ -203,6 +203,18 @@ __global__ void pack18_kernel(size_t npts, const double *f18, double *fpk)
     d[11] = 0.0;
 }
 
+// The 12th double of a packed point: the 11th field (qyy) of its latitude neighbour (i, j + 1), so that the sixth
+// 16-byte piece of a cell's (x0, y0) point holds that field for BOTH of its latitude corners and the cooperative
+// integrators read it with one LDS.128 (rwrt_rk45.cuh, RWRT_PAD_F10).  The last latitude row repeats its own value
+// (its neighbour index is clamped onto it, interpolation.py:116-119).  Nothing else reads this slot.
+__global__ void pack_pad_kernel(size_t npts, int nlat, double *fpk)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    const int j = (int)(i % (size_t)nlat);
+    fpk[i * NPK + 11] = fpk[(j + 1 < nlat ? i + 1 : i) * NPK + 10];
+}
+
 }  // namespace
 
 void launch_bs_ready(const BsArgs &a, cudaStream_t s)
@@ -212,6 +224,8 @@ void launch_bs_ready(const BsArgs &a, cudaStream_t s)
     bs_q_kernel<<<grid, 256, 0, s>>>(a, g);
     bs_d2_kernel<<<grid, 256, 0, s>>>(a, g);
     bs_pack_kernel<<<grid, 256, 0, s>>>(a, g);
+    const size_t npts = (size_t)a.nmember * (a.nlon + (a.xcyclic ? 1 : 0)) * a.nlat;
+    pack_pad_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(npts, a.nlat, a.fpk);
 }
 
 void launch_trig_tables(int nlat, const double *lat, double *coslat, double *sinlat, cudaStream_t s)
@@ -223,6 +237,7 @@ void launch_pack_from_fields18(int nmember, int nlon_f, int nlat, const double *
 {
     size_t npts = (size_t)nmember * nlon_f * nlat;
     pack18_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(npts, fields18, fpk);
+    pack_pad_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(npts, nlat, fpk);
 }
 
 }  // namespace rwrt

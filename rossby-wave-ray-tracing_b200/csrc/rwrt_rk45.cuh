@@ -664,103 +664,135 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 
-// Which 16-byte piece of a cell a quarter-warp lane copies.  A cell is two runs of 192 contiguous bytes in the point
-// table -- points (x0,y0),(x0,y1) and, one longitude row further, (x1,y0),(x1,y1) -- and they are staged back to back
-// (c | a | d | b, 4 x 96 B), i.e. 24 pieces, piece p at byte 16 p of the staged record.
-//   RWRT_FETCH_MAP 0 (up to v20): lane q8 copies half (q8 & 1) of sector i = 0..2 of corner q8 >> 1: every instruction
-//     touches four separate 32-byte sectors per cell;
-//   RWRT_FETCH_MAP 1: instruction i copies pieces 8 i .. 8 i + 7: 128 contiguous bytes per quarter-warp (i = 1: 64 B of
-//     each run).  tools/experiments/ldgsts_map.cu (the gather alone, 11 cells per warp and stage, 12 warps per SM):
-//     112 -> 73 cycles of the L1 / shared-memory pipe per warp and stage (shared-memory wavefronts of the copies 9.4 -> 6.3
-//     per cell, L1 tag look-ups 10.5 -> 6 per cell).
-#ifndef RWRT_FETCH_MAP
-#define RWRT_FETCH_MAP 1
+// The warp-cooperative gather.  A cell is two runs of 192 contiguous bytes in the point table -- points (x0,y0),(x0,y1)
+// and, one longitude row further, (x1,y0),(x1,y1) -- staged back to back (c | a | d | b, 4 x 96 B): 24 pieces of 16 B,
+// piece p at byte 16 p of the staged record.  A quarter-warp copies one cell with three cp.async per lane:
+// instruction i moves pieces 8 i .. 8 i + 7, i.e. 128 contiguous bytes (i = 1: 64 B of each run).  Up to v20 lane q8
+// copied half (q8 & 1) of sector i of corner q8 >> 1, four separate 32-byte sectors per instruction;
+// tools/experiments/ldgsts_map.cu (the gather alone, 11 cells per warp and stage, 12 warps per SM): 112 -> 73 cycles of
+// the L1 / shared-memory pipe per warp and stage, shared-memory wavefronts of the copies 9.4 -> 6.3 per cell, L1 tag
+// look-ups 10.5 -> 6 per cell.  Every piece is addressed as point index x 96 B + a compile-time offset from ONE per-lane
+// base, so that a copy costs one IMAD.WIDE:
+//     piece q8      = base + 96 pi                                  (base = table + 16 q8)
+//     piece 8 + q8  = base + 96 (pi + d1) + 32       d1 = 1 for q8 < 4 (byte 128 + 16 q8 of run 0),
+//                                                    nlat - 1 for q8 >= 4 (byte 16 (q8 - 4) of run 1)
+//     piece 16 + q8 = base + 96 (pi + nlat) + 64     (byte 64 + 16 q8 of run 1)
+// Cells with a clamped far index (grid edge, NaN position; interpolation.py:116-119: x1 == x0 makes run 1 a copy of
+// run 0, y1 == y0 makes a run's second point its first) never enter the list: their owner lane copies its own 24
+// pieces (RWRT_FETCH_SELF; one in 10^5 stages), so the copy loop carries no clamp test (v21 paid it per trip).
+// RWRT_PAD_F10 (the 12th double of a table point holds the 11th field of its latitude neighbour, rwrt_bs.cu): the
+// owner reads the four 11th fields of its cell with two LDS.128 instead of four LDS.64, which conflict two-way on the
+// 400-byte rows (4 wavefronts each, like an LDS.128).  In a y-clamped cell the neighbour IS the point itself, so the
+// self copy writes that field into both halves of the piece.
+#ifndef RWRT_PAD_F10
+#define RWRT_PAD_F10 1
 #endif
-#if RWRT_FETCH_MAP == 0
-#define RWRT_FETCH_SETUP                                                                                             \
-    /* quarter-warp lane q8 copies 16-byte half (q8 & 1) of sector i = 0..2 of corner point q8 >> 1                 \
-       (0: (x0,y0)  1: (x0,y1)  2: (x1,y0)  3: (x1,y1)); 3 sectors x 32 B = one 96-byte point */                     \
-    const unsigned pf_dst = stage_u32 + (unsigned)((q8 >> 1) * 96 + (q8 & 1) * 16);                                  \
-    const unsigned pf_dx = (q8 & 4) ? (unsigned)p.g.nlat * NPK * 8 : 0u;  /* corners 2, 3 live one longitude row further */ \
-    const unsigned pf_dy = (q8 & 2) ? NPK * 8u : 0u;                      /* corners 1, 3 one point further */        \
-    const char *pf_src = reinterpret_cast<const char *>(p.g.fpk) + (q8 & 1) * 16 + pf_dx + pf_dy;
-#define RWRT_FETCH_COPY(e)                                                                                           \
-    const char *sp = pf_src + (size_t)((e).x & 0x3fffffffu) * (NPK * 8);                                             \
-    if ((e).x >> 30) {                                                      /* clamped: the far corner is the near one */ \
-        if ((e).x & 0x40000000u) sp -= pf_dx;                                                                        \
-        if ((e).x & 0x80000000u) sp -= pf_dy;                                                                        \
-    }                                                                                                                \
-    const unsigned dst = pf_dst + (e).y;                                                                             \
-    cp_async16(dst, sp, l2pol);                                                                                      \
-    cp_async16(dst + 32, sp + 32, l2pol);                                                                            \
-    cp_async16(dst + 64, sp + 64, l2pol);
+#ifndef RWRT_FETCH_UNROLL
+#define RWRT_FETCH_UNROLL 1          /* 1: not unrolled (38.08 ms on C2); 0: the compiler's choice, four times with remainder code \
+                                        (39.83 ms: a quarter-warp has about three list entries); 2: 38.90 ms */
+#endif
+#ifndef RWRT_H_OPAQUE
+#define RWRT_H_OPAQUE 1              /* the step h stays in a register pair: 38.09 -> 37.94 ms on C2 */
+#endif
+#if RWRT_FETCH_UNROLL == 1
+#define RWRT_FETCH_LOOP_PRAGMA _Pragma("unroll 1")
+#elif RWRT_FETCH_UNROLL == 2
+#define RWRT_FETCH_LOOP_PRAGMA _Pragma("unroll 2")
 #else
+#define RWRT_FETCH_LOOP_PRAGMA
+#endif
 #define RWRT_FETCH_SETUP                                                                                             \
-    /* pieces q8, 8 + q8, 16 + q8 (piece p < 12: run 0 at byte 16 p; p >= 12: run 1 at byte 16 (p - 12)), addressed  \
-       as point index x 96 B + a compile-time offset from ONE per-lane base, so that a copy costs one IMAD.WIDE:      \
-         piece q8      = base + 96 pi                                  (base = table + 16 q8)                        \
-         piece 8 + q8  = base + 96 (pi + d1) + 32       d1 = 1 for q8 < 4 (byte 128 + 16 q8 of run 0),               \
-                                                        nlat - 1 for q8 >= 4 (byte 16 (q8 - 4) of run 1)              \
-         piece 16 + q8 = base + 96 (pi + nlat) + 64     (byte 64 + 16 q8 of run 1) */                                \
     const unsigned pf_dst = stage_u32 + (unsigned)(q8 * 16);                                                         \
     const char *pf_src = reinterpret_cast<const char *>(p.g.fpk) + q8 * 16;                                          \
     unsigned pf_d1 = (q8 < 4) ? 1u : (unsigned)p.g.nlat - 1u;                                                        \
     asm volatile("" : "+r"(pf_d1), "+l"(pf_src));                           /* kept whole, not re-derived per copy */
-#define RWRT_FETCH_COPY(e)                                                                                           \
-    const unsigned pi = (e).x & 0x3fffffffu;                                                                         \
-    const unsigned dst = pf_dst + (e).y;                                                                             \
-    if (((e).x >> 30) == 0) {                                                                                        \
-        cp_async16(dst, pf_src + (size_t)pi * (NPK * 8), l2pol);                                                     \
-        cp_async16(dst + 128, pf_src + (size_t)(pi + pf_d1) * (NPK * 8) + 32, l2pol);                                \
-        cp_async16(dst + 256, pf_src + (size_t)(pi + (unsigned)p.g.nlat) * (NPK * 8) + 64, l2pol);                   \
-    } else {                                                                                                         \
-        /* clamped (grid edge, NaN position; interpolation.py:116-119): x1 == x0 makes run 1 a copy of run 0,        \
-           y1 == y0 makes a run's second point its first.  Rare; written from scratch so that it shares no register  \
-           with the common path. */                                                                                  \
-        const unsigned xs = ((e).x & 0x40000000u) ? 0u : (unsigned)p.g.nlat, ys = ((e).x & 0x80000000u) ? 0u : 1u;   \
-        int q8r = q8;                                                                                                \
-        asm volatile("" : "+r"(q8r));                                       /* or ptxas keeps this path's per-lane offsets \
-                                                                               in registers for the whole kernel */  \
-        _Pragma("unroll") for (int i_ = 0; i_ < 3; ++i_) {                                                           \
-            const int pc = 8 * i_ + q8r, r_ = pc >= 12 ? 1 : 0, o_ = (pc - 12 * r_) * 16, second = o_ >= 96 ? 1 : 0;  \
-            cp_async16(dst + 128 * i_,                                                                               \
-                       reinterpret_cast<const char *>(p.g.fpk) +                                                     \
-                           (size_t)(pi + (r_ ? xs : 0u) + (second ? ys : 0u)) * (NPK * 8) + (o_ - 96 * second),      \
-                       l2pol);                                                                                       \
-        }                                                                                                            \
+__device__ __forceinline__ void cp_async8(unsigned dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst_smem), "l"(src));
+}
+// the owner lane's own copy of a clamped cell (rare)
+__device__ __noinline__ void fetch_self(const double *fpk, int nlat, unsigned key, unsigned dst, unsigned long long l2pol)
+{
+    const unsigned pi = key & 0x3fffffffu;
+    const unsigned xs = (key & 0x40000000u) ? 0u : (unsigned)nlat, ys = (key & 0x80000000u) ? 0u : 1u;
+#pragma unroll 1
+    for (int pc = 0; pc < 24; ++pc) {
+        const int r = pc >= 12 ? 1 : 0, o = (pc - 12 * r) * 16, second = o >= 96 ? 1 : 0;
+        const char *src = reinterpret_cast<const char *>(fpk) + (size_t)(pi + (r ? xs : 0u) + (second ? ys : 0u)) * (NPK * 8) +
+                          (o - 96 * second);
+        if (RWRT_PAD_F10 && o == 80 && ys == 0u) {                         // (f10, f10 of the latitude neighbour = itself)
+            cp_async8(dst + 16 * pc, src);
+            cp_async8(dst + 16 * pc + 8, src);
+        } else {
+            cp_async16(dst + 16 * pc, src, l2pol);
+        }
     }
-#endif
+}
 
 // Warp-cooperative request for the four corner points of every lane's cell (used by rk45_integrate_coop and
 // rk4_integrate_coop; expects the kernels' local names: p, FULL, lane_id, grp, q8, member_pt, prev_key, fetch_list,
-// the per-lane copy constants of RWRT_FETCH_SETUP, l2pol and the outputs inr, x0, y0, x1, y1, sx, sy).
+// the per-lane copy constants of RWRT_FETCH_SETUP, l2pol and the outputs inr, x0, y0, sx, sy).
 #define RWRT_FETCH(LON, LAT)                                                                                         \
     {                                                                                                                \
         inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
-        locate<RWRT_FAST>(p.g, LON, inr ? (LAT) : 0.0, x0, y0, x1, y1, sx, sy);                                      \
+        unsigned clamp_;                                                                                             \
+        locate_cell<RWRT_FAST>(p.g, LON, inr ? (LAT) : 0.0, x0, y0, clamp_, sx, sy);                                 \
         /* what gets staged = point (x0, y0) AND the clamp pattern (interpolation.py:116-119: x1, y1 come from the   \
            UNCLAMPED index, so a NaN / out-of-range position can pair (x0, y0) with x1 == x0); both are in the key: \
            bits 0..29 point index in the table (all members), bit 30 x clamped, bit 31 y clamped */                  \
-        const unsigned key = (member_pt + (unsigned)(x0 * p.g.nlat + y0)) | (x1 == x0 ? 0x40000000u : 0u) |          \
-                             (y1 == y0 ? 0x80000000u : 0u);                                                          \
+        const unsigned key = (member_pt + (unsigned)(x0 * p.g.nlat + y0)) | clamp_;                                  \
         /* a ray often stays in its cell from one stage to the next: its corners are still staged, no new copy */   \
         const bool need = (key != prev_key);                                                                         \
-        const unsigned need_mask = __ballot_sync(FULL, need);                                                        \
+        const bool plain = need && clamp_ == 0u;                                                                     \
+        const unsigned need_mask = __ballot_sync(FULL, plain);                                                       \
         prev_key = key;                                                                                              \
-        /* compact list of the cells to fetch: (key, destination lane) */                                            \
-        if (need)                                                                                                    \
+        /* compact list of the cells to fetch: (point index, destination lane) */                                    \
+        if (plain)                                                                                                   \
             *reinterpret_cast<uint2 *>(fetch_list + __popc(need_mask & ((1u << lane_id) - 1u)) * CO_LIST_STRIDE) =   \
                 make_uint2(key, (unsigned)lane_id * CO_REC_STRIDE);                                                  \
+        if (need && clamp_ != 0u) fetch_self(p.g.fpk, p.g.nlat, key, stage_u32 + (unsigned)lane_id * CO_REC_STRIDE, l2pol); \
         __syncwarp();                                                                                                \
         const int nfetch = __popc(need_mask);                                                                        \
-        /* quarter-warp `grp` copies list entries grp, grp+4, ...: lane q8 moves 16-byte half (q8 & 1) of the three  \
-           sectors of corner q8 >> 1 -- 24 x 16 B per cell */                                                        \
+        /* quarter-warp `grp` copies list entries grp, grp + 4, ... */                                               \
+        RWRT_FETCH_LOOP_PRAGMA                                                                                       \
         for (int j = grp; j < nfetch; j += 4) {                                                                      \
             const uint2 e = *reinterpret_cast<const uint2 *>(fetch_list + j * CO_LIST_STRIDE);                       \
-            RWRT_FETCH_COPY(e)                                                                                       \
+            const unsigned dst = pf_dst + e.y;                                                                       \
+            cp_async16(dst, pf_src + (size_t)e.x * (NPK * 8), l2pol);                                                \
+            cp_async16(dst + 128, pf_src + (size_t)(e.x + pf_d1) * (NPK * 8) + 32, l2pol);                           \
+            cp_async16(dst + 256, pf_src + (size_t)(e.x + (unsigned)p.g.nlat) * (NPK * 8) + 64, l2pol);              \
         }                                                                                                            \
         asm volatile("cp.async.commit_group;\n" ::);                                                                 \
     }
+
+// The owner lane's blend of its staged cell (interpolation.py:132-133): a*wa + b*wb + c*wc + d*wd for the 11 fields;
+// corners c = (x0,y0) at byte 0, a = (x0,y1) at 96, d = (x1,y0) at 192, b = (x1,y1) at 288; fields 2k, 2k+1 per LDS.128.
+#if RWRT_PAD_F10
+#define RWRT_BLEND(f, rec, wa, wb, wc, wd)                                                                           \
+    _Pragma("unroll") for (int k_ = 0; k_ < 5; ++k_) {                                                               \
+        const double2 c2 = *reinterpret_cast<const double2 *>((rec) + k_ * 16);                                      \
+        const double2 a2 = *reinterpret_cast<const double2 *>((rec) + 96 + k_ * 16);                                 \
+        const double2 d2 = *reinterpret_cast<const double2 *>((rec) + 192 + k_ * 16);                                \
+        const double2 b2 = *reinterpret_cast<const double2 *>((rec) + 288 + k_ * 16);                                \
+        f[2 * k_] = a2.x * (wa) + b2.x * (wb) + c2.x * (wc) + d2.x * (wd);                                           \
+        f[2 * k_ + 1] = a2.y * (wa) + b2.y * (wb) + c2.y * (wc) + d2.y * (wd);                                       \
+    }                                                                                                                \
+    {   /* 11th field: (c, a) and (d, b) side by side in the sixth piece of c and d */                               \
+        const double2 ca = *reinterpret_cast<const double2 *>((rec) + 80);                                           \
+        const double2 db = *reinterpret_cast<const double2 *>((rec) + 192 + 80);                                     \
+        f[10] = ca.y * (wa) + db.y * (wb) + ca.x * (wc) + db.x * (wd);                                               \
+    }
+#else
+#define RWRT_BLEND(f, rec, wa, wb, wc, wd)                                                                           \
+    _Pragma("unroll") for (int k_ = 0; k_ < 6; ++k_) {                                                               \
+        const double2 c2 = *reinterpret_cast<const double2 *>((rec) + k_ * 16);                                      \
+        const double2 a2 = *reinterpret_cast<const double2 *>((rec) + 96 + k_ * 16);                                 \
+        const double2 d2 = *reinterpret_cast<const double2 *>((rec) + 192 + k_ * 16);                                \
+        const double2 b2 = *reinterpret_cast<const double2 *>((rec) + 288 + k_ * 16);                                \
+        f[2 * k_] = a2.x * (wa) + b2.x * (wb) + c2.x * (wc) + d2.x * (wd);                                           \
+        if (2 * k_ + 1 < 11) f[2 * k_ + 1] = a2.y * (wa) + b2.y * (wb) + c2.y * (wc) + d2.y * (wd);                  \
+    }
+#endif
 
 // OUT: what happens to an output row -- OUT_ROWS (stored: record or planes; the product path of rwrt_ray_run_rk45),
 // OUT_GRID (added to the ray-density / flux grids: rwrt_ray_sweep_grid, no trajectory is materialised at all), or both.
@@ -921,13 +953,18 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
         }
         double t_new = L.t + L.h_abs;  // rkf45.py:426-435
         if (t_new - tb > 0) t_new = tb;
+#if RWRT_H_OPAQUE
+        double h = active ? (t_new - L.t) : 0.0;
+        asm volatile("" : "+d"(h));                                        // kept in a register pair: ptxas recomputed it (DADD + 2 ISETP + 2 FSEL) twice per stage
+#else
         const double h = active ? (t_new - L.t) : 0.0;
+#endif
         double ys[5], kn[5], ug = 0, vg = 0, cos_new = 1.0;
         bool masked = false;
         // Software pipeline over the six stages: the cell record of stage s+1 is requested as soon as stage s
         // has produced its group velocity (d lon/dt, d lat/dt are all the next position needs); the copies fly
         // while stage s finishes dk/dt, dl/dt, dA/dt and stage s+1 evaluates its trigonometry and reciprocals.
-        int x0, y0, x1, y1;
+        int x0, y0;
         double sx, sy;
         bool inr;
         // stage 1 input (rkf45.py:306-311): y + (K_1 a_21) h
@@ -997,15 +1034,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
             }
             // blend (interpolation.py:132-133): a*wa + b*wb + c*wc + d*wd, fields k = 0..10
             double f[12];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {   // corners c = (x0,y0), a = (x0,y1), d = (x1,y0), b = (x1,y1); fields 2k, 2k+1
-                const double2 c2 = *reinterpret_cast<const double2 *>(my_rec + k * 16);
-                const double2 a2 = *reinterpret_cast<const double2 *>(my_rec + 96 + k * 16);
-                const double2 d2 = *reinterpret_cast<const double2 *>(my_rec + 192 + k * 16);
-                const double2 b2 = *reinterpret_cast<const double2 *>(my_rec + 288 + k * 16);
-                f[2 * k] = a2.x * wa_ + b2.x * wb + c2.x * wc + d2.x * wd_;
-                if (2 * k + 1 < 11) f[2 * k + 1] = a2.y * wa_ + b2.y * wb + c2.y * wc + d2.y * wd_;
-            }
+            RWRT_BLEND(f, my_rec, wa_, wb, wc, wd_)
             masked = err;
             Merc m = mercator_from_fields<RWRT_FAST>(f, tgp);
             rhs_position<RWRT_FAST>(m, yp, wr, kn, ug, vg);               // kn[0], kn[1], ug, vg
@@ -1287,7 +1316,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk4_integrate_coop(RunParams p)
     double plon = y[0], plat = y[1];
     const double dt = p.tstep;
     int code = (y[3] == y[3]) ? 1 : 0;
-    int x0, y0, x1, y1;
+    int x0, y0;
     double sx, sy, ug = 0, vg = 0;
     bool inr, m_first = false, m_any = false;
     // evaluation e of step it: e = 0 -> f(y) (only before the first step; afterwards FSAL), 1..3 -> k2..k4, 4 -> f(y_new)
@@ -1313,15 +1342,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk4_integrate_coop(RunParams p)
             wr.rden = wrden;
         }
         double f[12];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const double2 c2 = *reinterpret_cast<const double2 *>(my_rec + k * 16);
-            const double2 a2 = *reinterpret_cast<const double2 *>(my_rec + 96 + k * 16);
-            const double2 d2 = *reinterpret_cast<const double2 *>(my_rec + 192 + k * 16);
-            const double2 b2 = *reinterpret_cast<const double2 *>(my_rec + 288 + k * 16);
-            f[2 * k] = a2.x * wa_ + b2.x * wb + c2.x * wc + d2.x * wd_;
-            if (2 * k + 1 < 11) f[2 * k + 1] = a2.y * wa_ + b2.y * wb + c2.y * wc + d2.y * wd_;
-        }
+        RWRT_BLEND(f, my_rec, wa_, wb, wc, wd_)
         Merc m = mercator_from_fields<RWRT_FAST>(f, tgp);
         rhs_position<RWRT_FAST>(m, yp, wr, kn, ug, vg);
         rhs_wavenumber<RWRT_FAST>(m, yp, wr, kn);
@@ -1386,8 +1407,8 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk4_integrate_coop(RunParams p)
 }
 
 #undef RWRT_FETCH
-#undef RWRT_FETCH_COPY
 #undef RWRT_FETCH_SETUP
+#undef RWRT_BLEND
 
 }  // namespace RWRT_VARIANT
 }  // namespace rwrt

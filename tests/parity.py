@@ -79,31 +79,31 @@ def compare(got, got_accepted, ref, ref_accepted, nongrazing, label="", max_outl
                 steps_total=int(got_accepted.sum()), steps_total_ref=int(ref_accepted.sum()))
 
 
-def oracle_run(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, tstep_h=2.0):
+def oracle_run(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, tstep_h=2.0, xcyclic=True):
     """The C oracle on one batch: returns (dict name -> (nt,3,ns,nz), accepted)."""
     import rwrt_b200  # noqa: F401
     from rwrt_b200 import synthetic
     from oracle import oracle
     lon, lat = synthetic.grid_coords(*u.shape)
-    F = oracle.bs_ready(u, v, lat, True)
+    F = oracle.bs_ready(u, v, lat, xcyclic)
     nt = int(days * 86400.0 / (tstep_h * 3600.0)) + 1
     out = oracle.ray_init(F, lon, lat, slon_rad, slat_rad, zwn, freq, nt)
     acc, _ = oracle.ray_run_rk45(F, lon, lat, out, tstep_h * 3600.0, days * 86400.0)
     return {n: out[k] for k, n in enumerate(NAMES)}, acc
 
 
-def oracle_nongrazing(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, ref=None, acc=None):
+def oracle_nongrazing(u, v, slon_rad, slat_rad, zwn, days, freq=0.0, ref=None, acc=None, xcyclic=True):
     """Non-grazing mask from the oracle itself: the base run and four runs with the sources moved by
     +-1 ulp in longitude / latitude must agree to < 1e-7 deg, in NaN pattern and in step counts -- and, so that the
     auxiliary bar on the other state components (relative 1e-5 on k, l, A, u_g, v_g in `compare`) is asserted only
     where the oracle itself is insensitive, to 1e-6 relative in those components (over 60 days a ray can keep its
     position to 1e-7 deg while k or l next to a critical line already differ by 1e-4 between two oracle runs)."""
     if ref is None:
-        ref, acc = oracle_run(u, v, slon_rad, slat_rad, zwn, days, freq)
+        ref, acc = oracle_run(u, v, slon_rad, slat_rad, zwn, days, freq, xcyclic=xcyclic)
     ng = np.ones(acc.shape, dtype=bool)
     for a, b in ((np.nextafter(slon_rad, np.inf), slat_rad), (np.nextafter(slon_rad, -np.inf), slat_rad),
                  (slon_rad, np.nextafter(slat_rad, np.inf)), (slon_rad, np.nextafter(slat_rad, -np.inf))):
-        per, acc_p = oracle_run(u, v, a, b, zwn, days, freq)
+        per, acc_p = oracle_run(u, v, a, b, zwn, days, freq, xcyclic=xcyclic)
         for n in NAMES:
             ng &= np.all(np.isnan(ref[n]) == np.isnan(per[n]), axis=0)
         for n in ("rlon", "rlat"):

@@ -21,12 +21,12 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def make_wr(u, v, zwn, slon_rad, slat_rad, days, freq=0.0, tstep_h=2.0, **kw):
+def make_wr(u, v, zwn, slon_rad, slat_rad, days, freq=0.0, tstep_h=2.0, xcyclic=True, **kw):
     nlon, nlat = u.shape
     w = WR(len(zwn), len(slon_rad), tstep_h * 3600.0, days * 86400.0, freq, nx=nlon, ny=nlat, **kw)
     w.bs.lon, w.bs.lat = synthetic.grid_coords(nlon, nlat)
     w.bs.u, w.bs.v = u, v
-    w.bs.ready(xcyclic=True)
+    w.bs.ready(xcyclic=xcyclic)
     w.set_zwn(zwn)
     w.source_lon = np.asarray(slon_rad, dtype=np.float64)
     w.source_lat = np.asarray(slat_rad, dtype=np.float64)
@@ -177,6 +177,34 @@ def test_vs_oracle_medium(strict):
     assert st["nongrazing"] > 0.7 * st["live"]
     # whole-batch sanity: total accepted steps within 0.5 % of the oracle's even counting grazing rays
     assert abs(st["steps_total"] - st["steps_total_ref"]) < 1e-2 * st["steps_total_ref"]
+
+
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+def test_noncyclic_grid_clamped_cells(strict):
+    """xcyclic=False (the reference's own default, bs.py:318): no wrap column, so every position in the last longitude
+    cell has x1 clamped onto x0 (interpolation.py:116-119) -- the cells that the cooperative gather does not put on its
+    fetch list (their owner lane copies them itself).  2.5-degree Clim, 240 sources of which half start within 12
+    degrees west of the seam, k = 1..4, 8 days, against the oracle on its non-grazing set."""
+    u, v = synthetic.clim(144, 73)
+    rng = np.random.default_rng(2718)
+    sl = np.concatenate([rng.uniform(346.0, 359.9, 120), rng.uniform(0.0, 346.0, 120)])
+    sa = rng.uniform(-60.0, 60.0, 240)
+    slon, slat = np.radians(sl), np.radians(sa)
+    zwn = np.arange(1.0, 5.0)
+    ref, acc, ng = parity.oracle_nongrazing(u, v, slon, slat, zwn, 8.0, xcyclic=False)
+    # the case does what it is for: live rays spend output rows inside the clamped cell column
+    seam = np.radians(357.5)
+    with np.errstate(invalid="ignore"):
+        in_seam = (np.mod(ref["rlon"], 2 * np.pi) >= seam) & np.isfinite(ref["rmwn"])
+    assert in_seam[1:].sum() > 2000
+    w = make_wr(u, v, zwn, slon, slat, 8.0, xcyclic=False)
+    w.ray_run(mode="numpy", root_method="numpy", inte_method="rk45", strict=strict)
+    got = {n: getattr(w, n) for n in parity.NAMES}
+    st = parity.compare(got, w.accepted, ref, acc, ng, "noncyclic", max_outliers=0)
+    parity.record(f"2.5 deg Clim, xcyclic=False, 240 sources x k=1..4, 8 d vs oracle, {'strict' if strict else 'fast'}", st)
+    print(st)
+    assert st["nongrazing"] > 0.5 * st["live"]
+    assert (ng & in_seam[1:].any(axis=0)).sum() > 50              # ... and non-grazing rays among them
 
 
 def test_batch_composition_independence():

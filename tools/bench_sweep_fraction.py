@@ -32,7 +32,7 @@ def main():
     tot = torch.zeros(1, dtype=torch.int64, device=dev)
     times = (C.c_double * 4)()
     stats = (C.c_double * 3)()
-    for world in (1, 2, 4, 8, 16):
+    for world in [int(x) for x in os.environ.get("RWRT_SWEEP_FRACTIONS", "1,2,4,8,16").split(",")]:   # 1/world of the sources
         idx = np.arange(0, len(slon_all), world)
         sl = torch.from_numpy(slon_all[idx].copy()).to(dev)
         sa = torch.from_numpy(slat_all[idx].copy()).to(dev)
