@@ -691,6 +691,9 @@ __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.rel
 #define RWRT_FETCH_UNROLL 1          /* 1: not unrolled (38.08 ms on C2); 0: the compiler's choice, four times with remainder code \
                                         (39.83 ms: a quarter-warp has about three list entries); 2: 38.90 ms */
 #endif
+#ifndef RWRT_COMBO_TREE
+#define RWRT_COMBO_TREE 0
+#endif
 #ifndef RWRT_H_OPAQUE
 #define RWRT_H_OPAQUE 1              /* the step h stays in a register pair: 38.09 -> 37.94 ms on C2 */
 #endif
@@ -985,6 +988,22 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
 #if RWRT_TMEM_KS
             __syncwarp();
             if (s > 1) tm_wait_st();                                       // K_s of the previous stage has landed
+#if RWRT_COMBO_TREE
+            // a tree of direct branches instead of the jump table ptxas makes of a switch (LDC + BRX: the warp waits for the
+            // constant load, then for the indirect branch to resolve)
+            if (s <= 2) {
+                if (s < 2) tm_combo<1>(tk, k1, cC[2], part);
+                else tm_combo<2>(tk, k1, cC[3], part);
+            } else if (s <= 4) {
+                if (s < 4) tm_combo<3>(tk, k1, cC[4], part);
+                else tm_combo<4>(tk, k1, cC[5], part);
+            } else if (s < 6) {
+                tm_combo<5>(tk, k1, cC[6], part);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) part[c] = 0.0;
+            }
+#else
             switch (s) {
                 case 1: tm_combo<1>(tk, k1, cC[2], part); break;
                 case 2: tm_combo<2>(tk, k1, cC[3], part); break;
@@ -996,6 +1015,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
                     for (int c = 0; c < 5; ++c) part[c] = 0.0;
                     break;
             }
+#endif
 #else
 #define RWRT_PART(c) \
     switch (s) { \
