@@ -70,6 +70,28 @@ static __device__ __noinline__ double pymod_2pi_wrapped(double a)
 // np.maximum: NaN if either operand is NaN
 __device__ __forceinline__ double np_maximum(double a, double b) { return (a != a || b != b) ? qnan() : fmax(a, b); }
 
+// np.maximum(|a|, |b|) (the error scale, rkf45.py:443): the bit patterns of non-negative doubles order like integers and
+// every NaN pattern lies above +inf, so the integer maximum of the patterns IS the NaN-propagating maximum -- two integer
+// compares and two selects where fmax on doubles is emulated with ~9 instructions per component on sm_100.
+__device__ __forceinline__ double np_absmax(double a, double b)
+{
+    const long long ia = __double_as_longlong(a) & 0x7fffffffffffffffLL, ib = __double_as_longlong(b) & 0x7fffffffffffffffLL;
+    return __longlong_as_double(ia > ib ? ia : ib);
+}
+
+// x / sqrt(5) (rkf45.py:29-31), correctly rounded without the division routine (~18 instructions): with c = RN(sqrt 5),
+// y = RN(1 / c), q = RN(x y) and the exact remainder r = x - q c, RN(q + r y) is the correctly rounded quotient
+// (Markstein's final division step; checked against x / c on 2e5 random arguments with exact rational arithmetic).
+// inf is passed through (the remainder would be NaN); NaN stays NaN.
+__device__ __forceinline__ double div_sqrt5(double x)
+{
+    const double c = 2.23606797749978969641, y = 0.44721359549995793928;   // 0x1.1e3779b97f4a8p+1, 0x1.c9f25c5bfedd9p-2
+    const double q = x * y;
+    const double r = fma(-q, c, x);
+    const double res = fma(r, y, q);
+    return (fabs(x) == __longlong_as_double(0x7ff0000000000000LL)) ? x : res;
+}
+
 // Bilinear sample of the packed fields (interpolation.py:103-135).  f[0..10].
 // interpolation.py:77-85 + 112-130: fractional indices, floor -> int32, clamp, weights from the CLAMPED indices
 template <bool FAST>
@@ -241,7 +263,12 @@ __device__ __forceinline__ double rcp_fast(double x)
 // steps y <- y (6 - a y^5) / 5 in double (quadratic: 2^-21 -> 2^-42 -> full), instead of the 166-instruction pow().
 __device__ __forceinline__ double pow_m02(double a)
 {
-    double y = (double)exp2f(-0.2f * __log2f((float)a));
+    // a lies in [5e-6, 2000] (step_factor): neither the logarithm's argument nor the exponential's needs the denormal
+    // / range handling of __log2f and exp2f (6 instructions); the bare MUFU results are the same bits there
+    float la, ex;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(la) : "f"((float)a));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-0.2f * la));
+    double y = (double)ex;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         double y2 = y * y;

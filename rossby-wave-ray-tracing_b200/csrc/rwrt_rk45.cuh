@@ -69,6 +69,17 @@ __device__ __forceinline__ double rms5(double a0, double a1, double a2, double a
     return sqrt(s) / sqrt(5.0);
 }
 
+// the same with the division by sqrt(5) as a correctly rounded three-instruction sequence (same bits)
+__device__ __forceinline__ double rms5_fast(double a0, double a1, double a2, double a3, double a4)
+{
+    double s = a0 * a0;
+    s = s + a1 * a1;
+    s = s + a2 * a2;
+    s = s + a3 * a3;
+    s = s + a4 * a4;
+    return div_sqrt5(sqrt(s));
+}
+
 // rkf45.py:34-99 select_initial_step (direction +1, error-estimator order 4)
 __device__ double initial_step(const Grid &g, const double *fb, const double *y0, const double *f0, double rtol,
                                double atol)
@@ -692,7 +703,7 @@ __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.rel
                                         (39.83 ms: a quarter-warp has about three list entries); 2: 38.90 ms */
 #endif
 #ifndef RWRT_COMBO_TREE
-#define RWRT_COMBO_TREE 0
+#define RWRT_COMBO_TREE 1
 #endif
 #ifndef RWRT_H_OPAQUE
 #define RWRT_H_OPAQUE 1              /* the step h stays in a register pair: 38.09 -> 37.94 ms on C2 */
@@ -1110,13 +1121,12 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
         double r[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {  // rkf45.py:442-446
-            // np.maximum propagates NaN (rkf45.py:443); in the fast build plain fmax is enough: whenever y_new[c] is
-            // NaN so is e[c] (the sum keeps its zero-coefficient terms), and the quotient below is NaN either way
-            double scale = p.atol + (RWRT_FAST ? fmax(fabs(L.y[c]), fabs(ys[c])) : np_maximum(fabs(L.y[c]), fabs(ys[c]))) * p.rtol;
+            // np.maximum propagates NaN (rkf45.py:443): np_absmax does, in both builds
+            double scale = p.atol + np_absmax(L.y[c], ys[c]) * p.rtol;
             const double e = ee[c];
             r[c] = RWRT_FAST ? (h * e) * rcp_fast(scale) : (h * e) / scale;   // scale >= atol > 0, never denormal
         }
-        double err = rms5(r[0], r[1], r[2], r[3], r[4]);
+        double err = RWRT_FAST ? rms5_fast(r[0], r[1], r[2], r[3], r[4]) : rms5(r[0], r[1], r[2], r[3], r[4]);
         if (err != err) err = 0;
         const bool accept = err < 1;
         double factor = step_factor(err, accept);
