@@ -234,9 +234,22 @@ __device__ __forceinline__ void sincos_halfpi(double x, double &sn, double &cs)
 
 // FAST-build sine of a small angle (the speed cut-off's sin(dlat/2), sin(dlon/2)): the fdlibm kernel polynomial
 // on |x| <= pi/4, the library routine beyond (rare: such a ray has moved > 90 degrees in one output interval).
+// Out-of-line library calls for the fast build's rare paths (a masked output point, a ray that moved > 90 degrees in
+// one output interval): inlined, libdevice's sin / cos / atan2 put ~1 000 instructions between the hot parts of the
+// integrator's attempt loop.
+#ifndef RWRT_COLD_OOL
+#define RWRT_COLD_OOL 1
+#endif
+#if RWRT_COLD_OOL
+#define RWRT_COLD static __device__ __noinline__
+#else
+#define RWRT_COLD static __device__ __forceinline__
+#endif
+RWRT_COLD double sin_cold(double x) { return sin(x); }
+RWRT_COLD double cos_cold(double x) { return cos(x); }
 __device__ __forceinline__ double sin_small(double x)
 {
-    if (!(fabs(x) <= 0.78539816339744830962)) return sin(x);
+    if (!(fabs(x) <= 0.78539816339744830962)) return sin_cold(x);
     const double z = x * x;
     double ps = fma(z, cSinCos[5], cSinCos[4]);
     ps = fma(z, ps, cSinCos[3]);
@@ -582,6 +595,7 @@ __device__ __forceinline__ void grid_add(unsigned long long *count, unsigned lon
 // FAST build of the speed cut-off test |2 atan2(sqrt a, sqrt(1-a))| >= cut (wr.py:97-112, 844-850):
 // the central angle is monotonic in a on [0, pi], so compare a with sin^2(cut/2); cos of both latitudes
 // are already known (cos_c from the last stage, cos_p cached from the previous output).
+RWRT_COLD double haversine_cold(double lon_c, double lat_c, double lon_p, double lat_p) { return haversine(lon_c, lat_c, lon_p, lat_p); }
 __device__ __forceinline__ bool speed_cutoff_fast(double lon_c, double lat_c, double lon_p, double lat_p, double cos_c,
                                                   double cos_p, double sin2_half_cut)
 {

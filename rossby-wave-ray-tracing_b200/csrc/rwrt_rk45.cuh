@@ -1163,7 +1163,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
             if (RWRT_FAST && !masked) {
                 too_fast = speed_cutoff_fast(L.y[0], L.y[1], L.plon, L.plat, cos_new, pcos, sin2_half_cut);
             } else {
-                double dd = haversine(L.y[0], L.y[1], L.plon, L.plat);  // wr.py:844-850
+                double dd = RWRT_FAST ? haversine_cold(L.y[0], L.y[1], L.plon, L.plat) : haversine(L.y[0], L.y[1], L.plon, L.plat);  // wr.py:844-850
                 too_fast = fabs(dd) >= p.cut;
             }
             if (too_fast) {
@@ -1195,7 +1195,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
             }
             L.plon = L.y[0];
             L.plat = L.y[1];
-            pcos = masked ? cos(L.y[1]) : cos_new;
+            pcos = masked ? (RWRT_FAST ? cos_cold(L.y[1]) : cos(L.y[1])) : cos_new;
             ++L.it;
         }
         const bool finished = dead || L.it >= p.nt;
