@@ -103,6 +103,43 @@ def test_sampler_rhs_vs_reference():
     assert np.max(np.abs(got[ok] - orc[ok]) / np.maximum(np.abs(orc[ok]), 1e-12)) < 1e-10
 
 
+def adversarial_longitudes():
+    """Longitudes that stress np.remainder(lon, 2 pi) (bs.py:519, interpolation.py:80): both signs, many turns, exact
+    multiples of the double 2 pi and their neighbours, +-0, values that round to 2 pi, huge / inf / NaN."""
+    tp = 2.0 * np.pi
+    rng = np.random.default_rng(31415)
+    mult = np.arange(-40, 41, dtype=np.float64) * tp
+    near = np.concatenate([np.nextafter(mult, np.inf), np.nextafter(mult, -np.inf), mult])
+    tiny = np.array([0.0, -0.0, 5e-324, -5e-324, 1e-300, -1e-300, 1e-20, -1e-20, np.nextafter(tp, 0.0), -np.nextafter(tp, 0.0)])
+    big = np.array([1e9, -1e9, 1e9 + 1.0, 3.7e12, -8.1e15, 1.2e300, np.inf, -np.inf, np.nan])
+    return np.concatenate([rng.uniform(-60.0, 60.0, 3000), rng.uniform(-1e6, 1e6, 500), near, tiny, big,
+                           mult[:, None].repeat(3, 1).ravel() + rng.uniform(0.0, tp, 243)])
+
+
+def test_rhs_on_adversarial_longitudes():
+    """The longitude wrap of the sampler (round 2: evaluated on the signed value with one fused multiply-add, general
+    routine only outside [0, 2 pi)) against the oracle's fmod-based np.remainder on longitudes chosen to break it: a
+    wrong quotient or sign rule puts the sample in another cell (O(1) differences), so the comparison is sharp."""
+    import torch
+    u, v = synthetic.clim(144, 73)
+    w = make_wr(u, v, [1.0], [0.1], [0.1], 1.0)
+    lon = adversarial_longitudes()
+    rng = np.random.default_rng(27)
+    n = lon.size
+    ys = np.stack([lon, np.radians(rng.uniform(-80.0, 80.0, n)), rng.uniform(1.0, 6.0, n), rng.uniform(-8.0, 8.0, n),
+                   np.ones(n)], axis=1)                                  # (lon, lat, k, l, A) as the ray state holds them
+    orc = oracle.rhs(oracle.bs_ready(u, v, w.bs.lat, True), w.bs.lon, w.bs.lat, ys)
+    assert np.isfinite(orc).all(axis=1).sum() > 0.9 * n                  # the case samples real cells, not NaN
+    y = torch.from_numpy(np.ascontiguousarray(ys.T)).cuda()
+    for flags in (lib.MODE_FAST, lib.MODE_STRICT):
+        dy = torch.empty_like(y)
+        lib.check(lib.load().rwrt_rhs(w.bs._h, n, lib.ptr(y), None, lib.ptr(dy), flags, lib.stream_ptr()))
+        got = dy.cpu().numpy().T
+        assert np.array_equal(np.isnan(got), np.isnan(orc))
+        ok = np.isfinite(orc)
+        assert np.max(np.abs(got[ok] - orc[ok]) / np.maximum(np.abs(orc[ok]), 1e-12)) < 1e-9
+
+
 TRAJ = ["c1_jet", "great_circle", "clim_g1", "clim_g1_freq", "clim_g2"]
 
 
