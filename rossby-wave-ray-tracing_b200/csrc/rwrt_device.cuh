@@ -103,10 +103,10 @@ __device__ __forceinline__ void locate(const Grid &g, double lon, double lat, in
     // what np.remainder returns, for either sign, in ONE rounding: for lon >= 0 it is fmod's exact result; for lon < 0
     // NumPy computes 2pi - fmod(|lon|, 2pi) = lon + (m + 1) 2pi (m = floor(|lon| / 2pi)), i.e. the same real number
     // rounded once, and q = -(m + 1).  A quotient that is off by one, an exact multiple of 2pi, a result that rounds
-    // to 2pi itself, huge / inf / NaN arguments all leave [0, 2pi) and take the general routine.  7 instructions
+    // to 2pi itself, huge / inf / NaN arguments all leave [0, 2pi) and take the general routine (NaN / inf give NaN either way and skip it).  7 instructions
     // instead of 35 on the path that every stage of every ray walks.
     double l2 = fma(-floor(lon * (1.0 / TWOPI)), TWOPI, lon);
-    if (!(l2 >= 0.0 && l2 < TWOPI)) {
+    if (!(l2 >= 0.0 && l2 < TWOPI) && l2 == l2) {                          // (NaN: lon is NaN or +-inf, and so is the remainder)
         l2 = pymod_2pi(lon);
         if (l2 >= TWOPI) l2 = 0.0;
     }
@@ -142,7 +142,9 @@ __device__ __forceinline__ void locate_cell(const Grid &g, double lon, double la
 {
 #if RWRT_LON_DIRECT
     double l2 = fma(-floor(lon * (1.0 / TWOPI)), TWOPI, lon);             // see locate()
-    if (!(l2 >= 0.0 && l2 < TWOPI)) {
+    // (a NaN here means lon is NaN or +-inf, and then the remainder is NaN as well: no call -- in the fixed-step RK4
+    // kernel, where the slots without a root run along as NaN, half of the lanes would take it in every evaluation)
+    if (!(l2 >= 0.0 && l2 < TWOPI) && l2 == l2) {
 #if RWRT_PYMOD_NOINLINE
         l2 = pymod_2pi_wrapped(lon);
 #else
