@@ -745,12 +745,12 @@ __device__ __noinline__ void fetch_self(const double *fpk, int nlat, unsigned ke
 
 // Warp-cooperative request for the four corner points of every lane's cell (used by rk45_integrate_coop and
 // rk4_integrate_coop; expects the kernels' local names: p, FULL, lane_id, grp, q8, member_pt, prev_key, fetch_list,
-// the per-lane copy constants of RWRT_FETCH_SETUP, l2pol and the outputs inr, x0, y0, sx, sy).
+// the per-lane copy constants of RWRT_FETCH_SETUP, FETCH_NANSKIP, l2pol and the outputs inr, x0, y0, sx, sy).
 #define RWRT_FETCH(LON, LAT)                                                                                         \
     {                                                                                                                \
         inr = fabs(LAT) <= HALFPI;                                          /* bs.py:787 */                          \
         unsigned clamp_;                                                                                             \
-        locate_cell<RWRT_FAST>(p.g, LON, inr ? (LAT) : 0.0, x0, y0, clamp_, sx, sy);                                 \
+        locate_cell<RWRT_FAST, FETCH_NANSKIP>(p.g, LON, inr ? (LAT) : 0.0, x0, y0, clamp_, sx, sy);                                 \
         /* what gets staged = point (x0, y0) AND the clamp pattern (interpolation.py:116-119: x1, y1 come from the   \
            UNCLAMPED index, so a NaN / out-of-range position can pair (x0, y0) with x1 == x0); both are in the key: \
            bits 0..29 point index in the table (all members), bit 30 x clamped, bit 31 y clamped */                  \
@@ -874,6 +874,7 @@ __global__ void RWRT_CO_BOUNDS rk45_integrate_coop(RunParams p)
     const unsigned long long l2pol = l2_policy_evict_last();
     unsigned char *fetch_list = stage + CO_LIST_OFS;                       // entry j at fetch_list + j * CO_LIST_STRIDE
     RWRT_FETCH_SETUP
+    constexpr bool FETCH_NANSKIP = false;                                  // a NaN ray is dropped at its next output row
 
     // Work items are (time quantum q, ray r), handed out q-major by one global counter: a ray is integrated a quantum
     // of output rows at a time, parked (state saved, progress flag set) and picked up again -- by whichever lane is
@@ -1332,6 +1333,7 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rk4_integrate_coop(RunParams p)
     const unsigned long long l2pol = l2_policy_evict_last();
     unsigned char *fetch_list = stage + CO_LIST_OFS;
     RWRT_FETCH_SETUP
+    constexpr bool FETCH_NANSKIP = true;                                   // no-root slots run along as NaN for all nt - 1 steps
     unsigned prev_key = 0xffffffffu;
 
     long long slot = (long long)blockIdx.x * blockDim.x + tid;
