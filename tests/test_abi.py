@@ -147,8 +147,8 @@ def test_host_expand_rows_equals_restatement(L, monkeypatch, isa, nslot, nt, b, 
 
 
 def test_stage_loop_of_the_integrator_has_no_divergence_guards(L):
-    """Code-generation guard (CPU, via cuobjdump): the stage loop of fast::rk45_integrate_coop must contain no
-    WARPSYNC.ALL / BRA.DIV.  When ptxas cannot prove the warp converged there (an early `continue`, a `trap` or a second
+    """Code-generation guard (CPU, via cuobjdump; tools/sass_loop.py prints the same view): the stage loop of
+    fast::rk45_integrate_coop must contain no WARPSYNC.ALL / BRA.DIV.  When ptxas cannot prove the warp converged there (an early `continue`, a `trap` or a second
     exit test in the refill section did that in round 2), it guards every __syncwarp / tcgen05 instruction of the loop and
     the kernel loses 9 % with bit-identical results -- invisible to every parity test."""
     import shutil
@@ -175,3 +175,11 @@ def test_stage_loop_of_the_integrator_has_no_divergence_guards(L):
         guards = [t for t in body if "WARPSYNC" in t or "BRA.DIV" in t]
         assert not guards, f"OUT={out_mode}: {len(guards)} divergence guards in the stage loop: {guards[:3]}"
         assert sum("DFMA" in t for t in body) > 100 and sum("LDGSTS" in t for t in body) >= 3
+        # ... and the properties the late round-2 kernel versions were measured on (profiles/r2_integrator_experiments.txt),
+        # each worth 1-5 % with bit-identical results:
+        assert len(body) < 600, f"stage loop grew to {len(body)} instructions (v23: 527; an unrolled copy loop was 733 and 4.5 % slower)"
+        assert sum("LDGSTS" in t for t in body) == 3, "the gather's copy loop must stay rolled (three cp.async per trip)"
+        assert sum("LDS.128" in t for t in body) == 22 and sum("LDS.64" in t for t in body) <= 1, \
+            "the staged cell is read with 22 LDS.128 (an LDS.64 conflicts two-way on the 400-byte rows)"
+        assert not any("BRX" in t for t in body), "the stage combinations go through direct branches, not a jump table"
+        assert not any("DSETP.MAX" in t or "DSETP.MIN" in t for t in body), "no emulated fp64 min / max in the stage loop"
