@@ -690,7 +690,7 @@ __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.rel
 //     piece 16 + q8 = base + 96 (pi + nlat) + 64     (byte 64 + 16 q8 of run 1)
 // Cells with a clamped far index (grid edge, NaN position; interpolation.py:116-119: x1 == x0 makes run 1 a copy of
 // run 0, y1 == y0 makes a run's second point its first) never enter the list: their owner lane copies its own 24
-// pieces (RWRT_FETCH_SELF; one in 10^5 stages), so the copy loop carries no clamp test (v21 paid it per trip).
+// pieces (fetch_self; one in 10^5 stages on a cyclic grid), so the copy loop carries no clamp test (v21 paid it per trip).
 // RWRT_PAD_F10 (the 12th double of a table point holds the 11th field of its latitude neighbour, rwrt_bs.cu): the
 // owner reads the four 11th fields of its cell with two LDS.128 instead of four LDS.64, which conflict two-way on the
 // 400-byte rows (4 wavefronts each, like an LDS.128).  In a y-clamped cell the neighbour IS the point itself, so the
